@@ -1,0 +1,559 @@
+// nka_capi.cu -- the C-ABI of libnka_b200.so: handle management, kernel
+// dispatch, host<->device staging, the optional NCCL reduction of the partial
+// dot products, and introspection.  Declarations: include/*.h.
+//
+// There is deliberately no CPU implementation of accel_update in this library:
+// without a CUDA device every entry point that computes aborts with a message.
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/nka_b200.h"
+#include "nka_kernels.cuh"
+
+#define NKA_VERSION "nka_b200 0.1 (sm_100a)"
+
+[[noreturn]] static void nka_fail(const char* file, int line, const char* msg)
+{
+  // the reference's convention: "Assertion failed at file:line" then stop
+  // (src-F08/f90_assert.F90:37-47); we abort so the failure cannot be ignored.
+  fprintf(stderr, "nka_b200: %s:%d: %s\n", file, line, msg);
+  fflush(stderr);
+  abort();
+}
+
+#define NKA_REQUIRE(cond, msg) do { if (!(cond)) nka_fail(__FILE__, __LINE__, msg); } while (0)
+#define CUDA_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                 \
+    char b_[256]; snprintf(b_, sizeof b_, "%s failed: %s", #call, cudaGetErrorString(e_));      \
+    nka_fail(__FILE__, __LINE__, b_); } } while (0)
+
+// ---------------------------------------------------------------------------
+// kernel dispatch tables
+// ---------------------------------------------------------------------------
+typedef void (*PassAFn)(const double*, const double*, size_t, size_t, const NkaDevState*, double*, unsigned*, double*);
+typedef void (*PassBFn)(double*, double*, double*, size_t, size_t, const NkaDevState*);
+
+static PassAFn g_pass_a[NKA_MAXSLOT + 1][3];   // [NC][V]
+static PassBFn g_pass_b[NKA_MAXSLOT + 1][3];   // [NZ][V]
+
+template <int N> struct FillTables {
+  static void run() {
+    g_pass_a[N][1] = nka_pass_a<N, 1>;
+    g_pass_a[N][2] = nka_pass_a<N, 2>;
+    g_pass_b[N - 1][1] = nka_pass_b<N - 1, 1>;
+    g_pass_b[N - 1][2] = nka_pass_b<N - 1, 2>;
+    FillTables<N - 1>::run();
+  }
+};
+template <> struct FillTables<0> { static void run() {} };
+
+static bool g_tables_ready = false;
+static void ensure_tables()
+{
+  if (!g_tables_ready) { FillTables<NKA_MAXSLOT>::run(); g_tables_ready = true; }
+}
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved at run time so single-GPU users need no NCCL at all
+// ---------------------------------------------------------------------------
+struct Id128 { char bytes[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static bool nccl_load()
+{
+  if (g_nccl.lib) return true;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (g_nccl.lib) break;
+  }
+  if (!g_nccl.lib) return false;
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+  return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
+}
+static const int kNcclFloat64 = 8;   // ncclDouble
+static const int kNcclSum = 0;       // ncclSum
+
+// ---------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------
+enum { T_PASS_A = 0, T_STATE = 1, T_MAT = 2, T_PASS_B = 3, T_COMM = 4, T_NKIND = 5 };
+
+struct TimedSpan { cudaEvent_t beg, end; int kind; };
+
+struct nka_state {
+  size_t vlen = 0, ld = 0;
+  int mvec = 0;
+  double vtol = 0.01;
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  double* W = nullptr;          // (mvec+1) columns of ld doubles: raw cached inputs / differences
+  double* Z = nullptr;          // (mvec+1) columns of ld doubles: corrections
+  NkaDevState* S = nullptr;     // device
+  double* dots = nullptr;       // device, 2*NKA_MAXSLOT
+  double* partials = nullptr;   // device, max_grid * 2*NKA_MAXSLOT
+  unsigned* ticket = nullptr;   // device
+  double* fstage = nullptr;     // device staging for host callers, vlen doubles (lazy)
+  int max_grid = 0;
+  // host-side knowledge of the device list: exact `pending`, upper bound on its length
+  bool pending = false;
+  int ub_len = 0;
+  // distributed
+  void* comm = nullptr;
+  bool own_comm = false;
+  int nranks = 1, rank = 0;
+  // accounting
+  unsigned long long launches = 0;
+  bool timing = false;
+  std::vector<TimedSpan> spans;
+  std::vector<cudaEvent_t> free_events;
+  double t_ms[T_NKIND] = {0, 0, 0, 0, 0};
+  unsigned long long t_cnt[T_NKIND] = {0, 0, 0, 0, 0};
+  int occ_a[NKA_MAXSLOT + 1][3];
+  int occ_b[NKA_MAXSLOT + 1][3];
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != dev) CUDA_CHECK(cudaSetDevice(dev)); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+static cudaEvent_t get_event(NKA st)
+{
+  if (!st->free_events.empty()) { cudaEvent_t e = st->free_events.back(); st->free_events.pop_back(); return e; }
+  cudaEvent_t e;
+  CUDA_CHECK(cudaEventCreate(&e));
+  return e;
+}
+
+static void fold_timing(NKA st)
+{
+  if (st->spans.empty()) return;
+  CUDA_CHECK(cudaStreamSynchronize(st->stream));
+  for (const TimedSpan& sp : st->spans) {
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, sp.beg, sp.end));
+    st->t_ms[sp.kind] += ms;
+    st->t_cnt[sp.kind] += 1;
+    st->free_events.push_back(sp.beg);
+    st->free_events.push_back(sp.end);
+  }
+  st->spans.clear();
+}
+
+struct SpanScope {
+  NKA st; int kind; cudaEvent_t beg = nullptr;
+  SpanScope(NKA s, int k) : st(s), kind(k) {
+    if (st->timing) { beg = get_event(st); CUDA_CHECK(cudaEventRecord(beg, st->stream)); }
+  }
+  ~SpanScope() {
+    if (beg) {
+      cudaEvent_t end = get_event(st);
+      CUDA_CHECK(cudaEventRecord(end, st->stream));
+      st->spans.push_back({beg, end, kind});
+      if (st->spans.size() >= 8192) fold_timing(st);
+    }
+  }
+};
+
+static int grid_for(NKA st, int occ, size_t n, int V)
+{
+  const size_t nv = n / V;
+  size_t need = (nv + NKA_THREADS - 1) / NKA_THREADS;
+  if (need < 1) need = 1;
+  size_t full = (size_t)st->num_sms * (occ > 0 ? occ : 1);
+  size_t g = need < full ? need : full;
+  if (g > (size_t)st->max_grid) g = st->max_grid;
+  return (int)g;
+}
+
+static int occupancy_a(NKA st, int nc, int V)
+{
+  if (st->occ_a[nc][V] < 0) {
+    int nb = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_pass_a[nc][V], NKA_THREADS, 0));
+    st->occ_a[nc][V] = nb;
+  }
+  return st->occ_a[nc][V];
+}
+
+static int occupancy_b(NKA st, int nz, int V)
+{
+  if (st->occ_b[nz][V] < 0) {
+    int nb = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_pass_b[nz][V], NKA_THREADS, 0));
+    st->occ_b[nz][V] = nb;
+  }
+  return st->occ_b[nz][V];
+}
+
+// How many older Z columns pass B is expected to keep: exact unless a vtol drop
+// or the s == 0 guard fires on the device (pass B copes with any actual count).
+static int nz_expected(NKA st)
+{
+  int nz;
+  if (st->pending) nz = st->ub_len - 1 < st->mvec - 1 ? st->ub_len - 1 : st->mvec - 1;
+  else nz = st->ub_len;
+  return nz < 0 ? 0 : nz;
+}
+
+// ---------------------------------------------------------------------------
+// construction / destruction
+// ---------------------------------------------------------------------------
+extern "C" NKA nka_init_ex(size_t vlen, int mvec, double vtol, int device, void* stream)
+{
+  // preconditions: src-C/...c:217-219 ; src-F08/nka_type.F90:190-191,205
+  NKA_REQUIRE(mvec > 0, "nka_init: mvec must be > 0");
+  NKA_REQUIRE(mvec <= NKA_B200_MAX_MVEC, "nka_init: mvec > 32 is not supported by this build");
+  NKA_REQUIRE(vtol > 0.0, "nka_init: vtol must be > 0");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    nka_fail(__FILE__, __LINE__, "no CUDA device: libnka_b200 has no CPU compute path");
+  ensure_tables();
+
+  NKA st = new nka_state();
+  if (device < 0) CUDA_CHECK(cudaGetDevice(&device));
+  st->device = device;
+  DeviceGuard guard(device);
+  CUDA_CHECK(cudaDeviceGetAttribute(&st->num_sms, cudaDevAttrMultiProcessorCount, device));
+  st->vlen = vlen;
+  st->mvec = mvec;
+  st->vtol = vtol;
+  st->ld = ((vlen + 15) / 16) * 16;                 // 128-byte aligned columns
+  if (st->ld == 0) st->ld = 16;
+  if (stream) { st->stream = (cudaStream_t)stream; st->own_stream = false; }
+  else { CUDA_CHECK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking)); st->own_stream = true; }
+  for (int i = 0; i <= NKA_MAXSLOT; ++i)
+    for (int v = 0; v < 3; ++v) { st->occ_a[i][v] = -1; st->occ_b[i][v] = -1; }
+
+  const size_t colbytes = st->ld * sizeof(double);
+  const size_t poolbytes = colbytes * (size_t)(mvec + 1);
+  e = cudaMalloc(&st->W, poolbytes);
+  if (e == cudaSuccess) e = cudaMalloc(&st->Z, poolbytes);
+  if (e != cudaSuccess) {
+    char b[200];
+    snprintf(b, sizeof b, "nka_init: cannot allocate 2 x %zu bytes of device memory for the subspace: %s",
+             poolbytes, cudaGetErrorString(e));
+    nka_fail(__FILE__, __LINE__, b);
+  }
+  st->max_grid = st->num_sms * 8;
+  CUDA_CHECK(cudaMalloc(&st->S, sizeof(NkaDevState)));
+  CUDA_CHECK(cudaMalloc(&st->dots, 2 * NKA_MAXSLOT * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&st->partials, (size_t)st->max_grid * 2 * NKA_MAXSLOT * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&st->ticket, sizeof(unsigned)));
+  CUDA_CHECK(cudaMemsetAsync(st->ticket, 0, sizeof(unsigned), st->stream));
+  CUDA_CHECK(cudaMemsetAsync(st->dots, 0, 2 * NKA_MAXSLOT * sizeof(double), st->stream));
+  nka_init_kernel<<<1, 32, 0, st->stream>>>(st->S, mvec, vtol);
+  CUDA_CHECK(cudaGetLastError());
+  st->launches += 1;
+  st->pending = false;
+  st->ub_len = 0;
+  return st;
+}
+
+extern "C" NKA nka_init(int vlen, int mvec, double vtol, double (*dp)(int, double*, double*))
+{
+  NKA_REQUIRE(vlen >= 0, "nka_init: vlen must be >= 0");
+  NKA_REQUIRE(dp == NULL,
+              "nka_init: a host dot-product callback cannot run inside a CUDA kernel; pass NULL and use "
+              "nka_comm_init for a global (multi-GPU) reduction");
+  return nka_init_ex((size_t)vlen, mvec, vtol, -1, NULL);
+}
+
+extern "C" void nka_delete(NKA st)
+{
+  if (!st) return;
+  DeviceGuard guard(st->device);
+  cudaStreamSynchronize(st->stream);
+  for (const TimedSpan& sp : st->spans) { cudaEventDestroy(sp.beg); cudaEventDestroy(sp.end); }
+  for (cudaEvent_t ev : st->free_events) cudaEventDestroy(ev);
+  if (st->comm && st->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(st->comm);
+  cudaFree(st->W); cudaFree(st->Z); cudaFree(st->S); cudaFree(st->dots);
+  cudaFree(st->partials); cudaFree(st->ticket); cudaFree(st->fstage);
+  if (st->own_stream) cudaStreamDestroy(st->stream);
+  delete st;
+}
+
+// ---------------------------------------------------------------------------
+// the hot path
+// ---------------------------------------------------------------------------
+extern "C" void nka_accel_update_dev(NKA st, double* f)
+{
+  NKA_REQUIRE(st != NULL, "nka_accel_update: null handle");
+  NKA_REQUIRE(f != NULL || st->vlen == 0, "nka_accel_update: null vector");
+  DeviceGuard guard(st->device);
+  const size_t n = st->vlen;
+  const int V = (((uintptr_t)f) % 16 == 0) ? 2 : 1;
+  const int L = st->ub_len;
+
+  if (L > 0) {
+    const int grid = grid_for(st, occupancy_a(st, L, V), n, V);
+    {
+      SpanScope t(st, T_PASS_A);
+      g_pass_a[L][V]<<<grid, NKA_THREADS, 0, st->stream>>>(f, st->W, st->ld, n, st->S, st->partials, st->ticket, st->dots);
+      CUDA_CHECK(cudaGetLastError());
+      st->launches += 1;
+    }
+    if (st->comm) {
+      SpanScope t(st, T_COMM);
+      const int rc = g_nccl.AllReduce(st->dots, st->dots, 2 * NKA_MAXSLOT, kNcclFloat64, kNcclSum, st->comm, st->stream);
+      if (rc != 0) nka_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclAllReduce failed");
+    }
+  }
+  {
+    SpanScope t(st, T_STATE);
+    nka_state_kernel<<<1, 32, 0, st->stream>>>(st->S, st->dots);
+    CUDA_CHECK(cudaGetLastError());
+    st->launches += 1;
+  }
+  if (L >= 2) {
+    // a vtol drop or the s == 0 guard may have broken a chain; the kernel exits at once otherwise
+    SpanScope t(st, T_MAT);
+    const int grid = grid_for(st, 4, n, 1);
+    nka_materialise<<<grid, NKA_THREADS, 0, st->stream>>>(st->W, st->ld, n, st->S);
+    CUDA_CHECK(cudaGetLastError());
+    st->launches += 1;
+  }
+  {
+    const int nz = nz_expected(st);
+    const int grid = grid_for(st, occupancy_b(st, nz, V), n, V);
+    SpanScope t(st, T_PASS_B);
+    g_pass_b[nz][V]<<<grid, NKA_THREADS, 0, st->stream>>>(f, st->W, st->Z, st->ld, n, st->S);
+    CUDA_CHECK(cudaGetLastError());
+    st->launches += 1;
+  }
+  // list length: the pending slot (if any) became a pair, capacity mvec pairs, plus the new pending slot
+  if (st->pending) st->ub_len = L + 1 < st->mvec + 1 ? L + 1 : st->mvec + 1;
+  else st->ub_len = L + 1;
+  st->pending = true;
+}
+
+extern "C" void nka_accel_update_host(NKA st, double* f)
+{
+  NKA_REQUIRE(st != NULL, "nka_accel_update: null handle");
+  DeviceGuard guard(st->device);
+  const size_t bytes = st->vlen * sizeof(double);
+  if (!st->fstage) CUDA_CHECK(cudaMalloc(&st->fstage, bytes ? bytes : 16));
+  CUDA_CHECK(cudaMemcpyAsync(st->fstage, f, bytes, cudaMemcpyHostToDevice, st->stream));
+  nka_accel_update_dev(st, st->fstage);
+  CUDA_CHECK(cudaMemcpyAsync(f, st->fstage, bytes, cudaMemcpyDeviceToHost, st->stream));
+  CUDA_CHECK(cudaStreamSynchronize(st->stream));
+}
+
+extern "C" void nka_accel_update(NKA st, double* f)
+{
+  NKA_REQUIRE(st != NULL, "nka_accel_update: null handle");
+  cudaPointerAttributes attr;
+  cudaError_t e = cudaPointerGetAttributes(&attr, f);
+  if (e != cudaSuccess) { cudaGetLastError(); attr.type = cudaMemoryTypeUnregistered; }
+  if (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) nka_accel_update_dev(st, f);
+  else nka_accel_update_host(st, f);
+}
+
+extern "C" void nka_restart(NKA st)
+{
+  NKA_REQUIRE(st != NULL, "nka_restart: null handle");
+  DeviceGuard guard(st->device);
+  nka_restart_kernel<<<1, 32, 0, st->stream>>>(st->S);
+  CUDA_CHECK(cudaGetLastError());
+  st->launches += 1;
+  st->pending = false;
+  st->ub_len = 0;
+}
+
+extern "C" void nka_relax(NKA st)
+{
+  NKA_REQUIRE(st != NULL, "nka_relax: null handle");
+  if (!st->pending) return;                       // src-C/...c:470: nothing pending, nothing to do
+  DeviceGuard guard(st->device);
+  nka_relax_kernel<<<1, 32, 0, st->stream>>>(st->S);
+  CUDA_CHECK(cudaGetLastError());
+  st->launches += 1;
+  if (st->ub_len >= 2) {
+    const int grid = grid_for(st, 4, st->vlen, 1);
+    nka_materialise<<<grid, NKA_THREADS, 0, st->stream>>>(st->W, st->ld, st->vlen, st->S);
+    CUDA_CHECK(cudaGetLastError());
+    st->launches += 1;
+  }
+  st->pending = false;
+  st->ub_len -= 1;
+}
+
+// ---------------------------------------------------------------------------
+// queries
+// ---------------------------------------------------------------------------
+static void fetch_state(NKA st, NkaDevState* h)
+{
+  DeviceGuard guard(st->device);
+  CUDA_CHECK(cudaMemcpyAsync(h, st->S, sizeof(NkaDevState), cudaMemcpyDeviceToHost, st->stream));
+  CUDA_CHECK(cudaStreamSynchronize(st->stream));
+}
+
+extern "C" int nka_num_vec(NKA st)
+{
+  NKA_REQUIRE(st != NULL, "nka_num_vec: null handle");
+  static thread_local NkaDevState h;
+  fetch_state(st, &h);
+  int n = 0;
+  for (int k = h.first; k != NKA_NIL; k = h.next[k]) ++n;
+  return h.pending ? n - 1 : n;
+}
+
+extern "C" int nka_max_vec(NKA st) { NKA_REQUIRE(st != NULL, "nka_max_vec: null handle"); return st->mvec; }
+extern "C" int nka_vec_len(NKA st) { NKA_REQUIRE(st != NULL, "nka_vec_len: null handle"); return (int)st->vlen; }
+extern "C" size_t nka_vec_len64(NKA st) { NKA_REQUIRE(st != NULL, "nka_vec_len64: null handle"); return st->vlen; }
+extern "C" double nka_vec_tol(NKA st) { NKA_REQUIRE(st != NULL, "nka_vec_tol: null handle"); return st->vtol; }
+
+extern "C" void nka_set_vec_tol(NKA st, double vtol)
+{
+  NKA_REQUIRE(st != NULL, "nka_set_vec_tol: null handle");
+  NKA_REQUIRE(vtol > 0.0, "nka_set_vec_tol: vtol must be > 0");
+  DeviceGuard guard(st->device);
+  st->vtol = vtol;
+  nka_set_vtol_kernel<<<1, 32, 0, st->stream>>>(st->S, vtol);
+  CUDA_CHECK(cudaGetLastError());
+  st->launches += 1;
+}
+
+extern "C" int nka_defined(NKA st)
+{
+  if (!st || !st->W || !st->Z || !st->S) return 0;
+  static thread_local NkaDevState h;
+  fetch_state(st, &h);
+  if (h.mvec != st->mvec) return 0;
+  return nka_state_defined(h);
+}
+
+extern "C" void nka_get_state(NKA st, nka_state_view* out)
+{
+  NKA_REQUIRE(st != NULL && out != NULL, "nka_get_state: null argument");
+  static thread_local NkaDevState h;
+  fetch_state(st, &h);
+  memset(out, 0, sizeof *out);
+  const int n = h.mvec + 1;
+  out->mvec = h.mvec; out->subspace = h.subspace; out->pending = h.pending;
+  out->first = h.first; out->last = h.last; out->free_slot = h.free_;
+  for (int k = 0; k < n; ++k) {
+    out->next[k] = h.next[k]; out->prev[k] = h.prev[k]; out->chained[k] = h.chained[k];
+    out->c[k] = h.c[k]; out->s[k] = h.s[k];
+    for (int j = 0; j < n; ++j) out->h[k * n + j] = h.h[k * NKA_MAXSLOT + j];
+  }
+  out->ndrop_last = h.ndrop_last; out->evicted_last = h.evicted_last; out->relaxed_last = h.relaxed_last;
+  out->error = h.error; out->vtol = h.vtol; out->min_margin = h.min_margin; out->s_last = h.s_last;
+  out->ncalls = h.ncalls;
+}
+
+extern "C" void nka_set_stream(NKA st, void* stream)
+{
+  NKA_REQUIRE(st != NULL, "nka_set_stream: null handle");
+  DeviceGuard guard(st->device);
+  fold_timing(st);
+  CUDA_CHECK(cudaStreamSynchronize(st->stream));
+  if (st->own_stream) { cudaStreamDestroy(st->stream); st->own_stream = false; }
+  if (stream) st->stream = (cudaStream_t)stream;
+  else { CUDA_CHECK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking)); st->own_stream = true; }
+}
+
+extern "C" void* nka_get_stream(NKA st) { NKA_REQUIRE(st != NULL, "nka_get_stream: null handle"); return (void*)st->stream; }
+
+extern "C" void nka_synchronize(NKA st)
+{
+  NKA_REQUIRE(st != NULL, "nka_synchronize: null handle");
+  DeviceGuard guard(st->device);
+  CUDA_CHECK(cudaStreamSynchronize(st->stream));
+}
+
+extern "C" unsigned long long nka_launch_count(NKA st) { NKA_REQUIRE(st != NULL, "nka_launch_count: null handle"); return st->launches; }
+
+extern "C" void nka_timing_enable(NKA st, int on)
+{
+  NKA_REQUIRE(st != NULL, "nka_timing_enable: null handle");
+  DeviceGuard guard(st->device);
+  if (!on) fold_timing(st);
+  st->timing = on != 0;
+}
+
+extern "C" void nka_timing_reset(NKA st)
+{
+  NKA_REQUIRE(st != NULL, "nka_timing_reset: null handle");
+  DeviceGuard guard(st->device);
+  fold_timing(st);
+  for (int k = 0; k < T_NKIND; ++k) { st->t_ms[k] = 0.0; st->t_cnt[k] = 0; }
+}
+
+extern "C" void nka_timing_read(NKA st, double ms[5], unsigned long long count[5])
+{
+  NKA_REQUIRE(st != NULL, "nka_timing_read: null handle");
+  DeviceGuard guard(st->device);
+  fold_timing(st);
+  for (int k = 0; k < T_NKIND; ++k) { ms[k] = st->t_ms[k]; count[k] = st->t_cnt[k]; }
+}
+
+extern "C" void nka_launch_geometry(NKA st, int* grid_a, int* grid_b, int* threads)
+{
+  NKA_REQUIRE(st != NULL, "nka_launch_geometry: null handle");
+  DeviceGuard guard(st->device);
+  const int L = st->ub_len;
+  if (grid_a) *grid_a = L > 0 ? grid_for(st, occupancy_a(st, L, 2), st->vlen, 2) : 0;
+  const int nz = nz_expected(st);
+  if (grid_b) *grid_b = grid_for(st, occupancy_b(st, nz, 2), st->vlen, 2);
+  if (threads) *threads = NKA_THREADS;
+}
+
+extern "C" const char* nka_b200_version(void) { return NKA_VERSION; }
+
+// ---------------------------------------------------------------------------
+// multi-GPU
+// ---------------------------------------------------------------------------
+extern "C" int nka_comm_unique_id(void* id128)
+{
+  if (!nccl_load()) return -1;
+  return g_nccl.GetUniqueId(id128);
+}
+
+extern "C" int nka_comm_init(NKA st, int nranks, int rank, const void* id128)
+{
+  NKA_REQUIRE(st != NULL && id128 != NULL, "nka_comm_init: null argument");
+  NKA_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "nka_comm_init: bad rank/nranks");
+  if (!nccl_load()) return -1;
+  DeviceGuard guard(st->device);
+  Id128 id;
+  memcpy(id.bytes, id128, sizeof id.bytes);
+  void* comm = nullptr;
+  const int rc = g_nccl.CommInitRank(&comm, nranks, id, rank);
+  if (rc != 0) return rc;
+  st->comm = comm; st->own_comm = true; st->nranks = nranks; st->rank = rank;
+  return 0;
+}
+
+extern "C" void nka_comm_adopt(NKA st, void* nccl_comm, int nranks, int rank)
+{
+  NKA_REQUIRE(st != NULL, "nka_comm_adopt: null handle");
+  NKA_REQUIRE(nccl_load(), "nka_comm_adopt: libnccl.so.2 not found");
+  st->comm = nccl_comm; st->own_comm = false; st->nranks = nranks; st->rank = rank;
+}

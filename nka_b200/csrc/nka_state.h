@@ -1,0 +1,373 @@
+// nka_state.h -- the small, scalar half of accel_update: list bookkeeping,
+// Gram row, Cholesky refactorisation, capacity eviction, vtol drop test,
+// triangular solves, and the "plans" that tell the two streaming kernels which
+// columns to touch.  Runs on the device in one thread of one warp
+// (nka_state_kernel); written as plain C++ behind NKA_HD so the GPU-less build
+// box can exercise the same logic in a test-only host model (tests/model/).
+//
+// Reference being replaced (same arithmetic order, so drop decisions agree):
+//   src-C/nonlinear_krylov_accelerator.c:295-443   src-F08/nka_type.F90:263-417
+//   relax  src-C/...c:466-485   restart  src-C/...c:447-463
+//
+// Storage model ("raw chain"):
+//   W[k] (k = list slot) holds the RAW input f cached when slot k was created,
+//   for as long as slot k is `chained`; the reference's normalised difference
+//   is  w_k = (W[k] - W[prev[k]]) / s[k].  A slot whose newer neighbour leaves
+//   the list is "materialised": W[k] <- W[k] - W[prev k], chained[k] = 0, and
+//   from then on w_k = W[k] / s[k].
+//   Z[k] holds, for the pending slot, Y = f_out - f_in of the call that created
+//   it; for a finished pair, Z'_k = Y_k + f_next, so that
+//   v_k - w_k = Z[k] / s[k]   (reference v, w: src-C/...c:316-320, :423).
+#pragma once
+
+#if defined(__CUDACC__)
+#define NKA_HD __host__ __device__ __forceinline__
+#else
+#define NKA_HD inline
+#endif
+
+#ifndef NKA_MAXSLOT
+#define NKA_MAXSLOT 33   // mvec <= 32
+#endif
+#define NKA_NIL (-1)
+
+#if defined(__CUDA_ARCH__)
+#define NKA_SQRT(x) sqrt(x)
+#else
+#include <cmath>
+#define NKA_SQRT(x) std::sqrt(x)
+#endif
+
+// Which stored columns pass A streams, in list order (newest first), and how
+// each difference is formed:  d_j = W[col[j]] - (bit j of submask ? prev : 0),
+// prev = f for j == 0, W[col[j-1]] otherwise.
+struct NkaPlanA {
+  int ncol;
+  unsigned submask;
+  int col[NKA_MAXSLOT];
+};
+
+// In-place conversions W[dst] -= W[sub], executed oldest first, before pass B.
+struct NkaPlanM {
+  int n;
+  int dst[NKA_MAXSLOT];
+  int sub[NKA_MAXSLOT];
+};
+
+// What pass B does:  Z[pslot] <- Z[pslot] + f (if has_pair);
+//   y = coef_p * Z[pslot] + sum_k coef[k] * Z[zcol[k]];
+//   Z[newslot] <- y;  W[newslot] <- f;  f <- f + y (if write_f).
+struct NkaPlanB {
+  int newslot;
+  int has_pair;
+  int pslot;
+  int write_f;
+  int nz;
+  int zcol[NKA_MAXSLOT];
+  double coef_p;
+  double coef[NKA_MAXSLOT];
+};
+
+struct NkaDevState {
+  // --- the reference's state (0-based slots, NKA_NIL terminates lists)
+  int mvec;
+  int subspace, pending;
+  int first, last, free_;
+  int next[NKA_MAXSLOT], prev[NKA_MAXSLOT];
+  double vtol;
+  double h[NKA_MAXSLOT * NKA_MAXSLOT];   // h[r*NKA_MAXSLOT + c]; raw Gram at (newer,older), factor at (older,newer)
+  double c[NKA_MAXSLOT];
+  // --- raw-chain bookkeeping
+  double s[NKA_MAXSLOT];                 // norm of the raw difference of pair k
+  int chained[NKA_MAXSLOT];
+  // --- plans
+  NkaPlanA planA;
+  NkaPlanM planM;
+  NkaPlanB planB;
+  // --- diagnostics of the last update (parity tests compare these with the oracle)
+  int ndrop_last, evicted_last, relaxed_last;
+  double min_margin;
+  double s_last;
+  unsigned long long ncalls;
+  int error;                             // nonzero: an internal invariant failed
+};
+
+#define NKA_H(S, r, c_) ((S).h[(r) * NKA_MAXSLOT + (c_)])
+
+NKA_HD void nka_build_plan_a(NkaDevState& S)
+{
+  NkaPlanA& A = S.planA;
+  int j = 0;
+  unsigned mask = 0;
+  for (int k = S.first; k != NKA_NIL; k = S.next[k], ++j) {
+    A.col[j] = k;
+    if (j == 0 ? S.pending : S.chained[k]) mask |= (1u << j);
+  }
+  A.ncol = j;
+  A.submask = mask;
+}
+
+NKA_HD void nka_state_restart(NkaDevState& S)
+{
+  // src-C/...c:447-463
+  S.first = NKA_NIL;
+  S.last = NKA_NIL;
+  S.subspace = 0;
+  S.pending = 0;
+  S.free_ = 0;
+  for (int k = 0; k < S.mvec; ++k) S.next[k] = k + 1;
+  S.next[S.mvec] = NKA_NIL;
+  for (int k = 0; k <= S.mvec; ++k) { S.prev[k] = NKA_NIL; S.chained[k] = 0; }
+  S.planM.n = 0;
+  nka_build_plan_a(S);
+}
+
+NKA_HD void nka_state_init(NkaDevState& S, int mvec, double vtol)
+{
+  S.mvec = mvec;
+  S.vtol = vtol;
+  S.ncalls = 0;
+  S.error = 0;
+  S.ndrop_last = S.evicted_last = S.relaxed_last = 0;
+  S.min_margin = 0.0;
+  S.s_last = 0.0;
+  for (int i = 0; i < NKA_MAXSLOT * NKA_MAXSLOT; ++i) S.h[i] = 0.0;
+  for (int i = 0; i < NKA_MAXSLOT; ++i) { S.c[i] = 0.0; S.s[i] = 1.0; }
+  S.planB.newslot = 0; S.planB.has_pair = 0; S.planB.pslot = 0; S.planB.write_f = 0; S.planB.nz = 0;
+  S.planB.coef_p = 0.0;
+  nka_state_restart(S);
+}
+
+// List surgery of relax(): src-C/...c:470-484.  Returns the removed slot or NIL.
+NKA_HD int nka_list_relax(NkaDevState& S)
+{
+  if (!S.pending) return NKA_NIL;
+  const int head = S.first;
+  S.first = S.next[head];
+  if (S.first == NKA_NIL) S.last = NKA_NIL;
+  else S.prev[S.first] = NKA_NIL;
+  S.next[head] = S.free_;
+  S.free_ = head;
+  S.pending = 0;
+  return head;
+}
+
+// Every surviving chained pair at a position after `jr` (positions refer to the
+// list as pass A saw it: ord[0..L-1]) loses its newer neighbour's raw column,
+// so it is converted in place, oldest first.  removed[slot] marks slots that
+// left the list during this call.
+NKA_HD void nka_plan_materialise(NkaDevState& S, const int* ord, int L, int jr, const bool* removed)
+{
+  NkaPlanM& M = S.planM;
+  M.n = 0;
+  for (int j = L - 1; j > jr; --j) {
+    const int k = ord[j];
+    if (S.chained[k]) {
+      if (!removed[k]) {
+        M.dst[M.n] = k;
+        M.sub[M.n] = ord[j - 1];
+        ++M.n;
+      }
+      S.chained[k] = 0;
+    }
+  }
+}
+
+// relax() as a host-requested operation between updates.
+NKA_HD void nka_state_relax(NkaDevState& S)
+{
+  S.planM.n = 0;
+  if (S.pending) {
+    int ord[NKA_MAXSLOT];
+    bool removed[NKA_MAXSLOT];
+    const int L = S.planA.ncol;
+    for (int j = 0; j < L; ++j) ord[j] = S.planA.col[j];
+    for (int k = 0; k < NKA_MAXSLOT; ++k) removed[k] = false;
+    const int head = nka_list_relax(S);
+    removed[head] = true;
+    nka_plan_materialise(S, ord, L, 0, removed);
+  }
+  nka_build_plan_a(S);
+}
+
+// The scalar part of one accel_update.  `dots` holds what pass A reduced, laid
+// out as dd[j] = d_0 . d_j  (j < ncol)  followed by  fd[j] = f . d_j  at
+// dots[stride + j]; ignored when the list was empty on entry.
+NKA_HD void nka_state_step(NkaDevState& S, const double* dots, int stride)
+{
+  int ord[NKA_MAXSLOT];
+  bool removed[NKA_MAXSLOT];
+  double rhs[NKA_MAXSLOT];
+  const int L = S.planA.ncol;
+  for (int j = 0; j < L; ++j) ord[j] = S.planA.col[j];
+  for (int k = 0; k < NKA_MAXSLOT; ++k) { removed[k] = false; rhs[k] = 0.0; }
+  const double* dd = dots;
+  const double* fd = dots + stride;
+
+  S.ndrop_last = 0;
+  S.evicted_last = 0;
+  S.relaxed_last = 0;
+  S.min_margin = 1.0e300;
+  S.s_last = 0.0;
+  S.planM.n = 0;
+  int jr = L;            // first list position whose slot left the list this call
+  int has_pair = 0;
+  double s = 0.0;
+
+  // Step A: norm of the new difference; zero guard.  src-C/...c:295-311
+  if (S.pending) {
+    s = NKA_SQRT(dd[0]);
+    S.s_last = s;
+    if (s == 0.0) {
+      removed[nka_list_relax(S)] = true;
+      S.relaxed_last = 1;
+      jr = 0;
+    }
+  }
+
+  // Step B: Gram row, refactorisation, drops.  src-C/...c:313-385
+  if (S.pending) {
+    const int p = S.first;
+    S.s[p] = s;
+    S.chained[p] = 1;
+    has_pair = 1;
+    // <w_1, w_k> = (d_0 . d_k) / (s s_k); the reference normalises first (:317-324)
+    for (int j = 1; j < L; ++j) {
+      const int k = ord[j];
+      NKA_H(S, p, k) = (dd[j] / s) / S.s[k];
+    }
+    int nvec = 1;
+    NKA_H(S, p, p) = 1.0;
+    const double tol2 = S.vtol * S.vtol;
+    int pos = 1;                                   // list position of k as pass A saw it
+    for (int k = S.next[p]; k != NKA_NIL; k = S.next[k], ++pos) {
+      if (++nvec > S.mvec) {                       // :339-347
+        if (S.last != k) S.error = 1;
+        S.next[S.last] = S.free_;
+        S.free_ = k;
+        S.last = S.prev[k];
+        S.next[S.last] = NKA_NIL;
+        removed[k] = true;
+        if (pos < jr) jr = pos;
+        S.evicted_last = 1;
+        break;
+      }
+      double hkk = 1.0;                            // :350-360
+      for (int j = p; j != k; j = S.next[j]) {
+        double hkj = NKA_H(S, j, k);
+        for (int i = p; i != j; i = S.next[i]) hkj -= NKA_H(S, k, i) * NKA_H(S, j, i);
+        hkj /= NKA_H(S, j, j);
+        NKA_H(S, k, j) = hkj;
+        hkk -= hkj * hkj;
+      }
+      if (hkk - tol2 < S.min_margin) S.min_margin = hkk - tol2;
+      if (hkk > tol2) {                            // :362-363
+        NKA_H(S, k, k) = NKA_SQRT(hkk);
+      } else {                                     // :364-379
+        const int pk = S.prev[k], nk = S.next[k];
+        S.next[pk] = nk;
+        if (nk == NKA_NIL) S.last = pk;
+        else S.prev[nk] = pk;
+        S.next[k] = S.free_;
+        S.free_ = k;
+        removed[k] = true;
+        if (pos < jr) jr = pos;
+        k = pk;
+        --nvec;
+        ++S.ndrop_last;
+      }
+    }
+    S.subspace = 1;
+    S.pending = 0;
+  }
+
+  // Pairs that lost their newer neighbour are converted before pass B overwrites anything.
+  if (jr < L) nka_plan_materialise(S, ord, L, jr, removed);
+
+  // Step C: storage for the new vectors.  src-C/...c:391-394
+  if (S.free_ == NKA_NIL) { S.error = 2; return; }
+  const int nw = S.free_;
+  S.free_ = S.next[nw];
+
+  // Step D: projection.  src-C/...c:400-417
+  NkaPlanB& B = S.planB;
+  B.newslot = nw;
+  B.has_pair = has_pair;
+  B.pslot = has_pair ? S.first : 0;
+  B.coef_p = 0.0;
+  B.nz = 0;
+  B.write_f = 0;
+  if (S.subspace) {
+    for (int j = 0; j < L; ++j) rhs[ord[j]] = fd[j] / S.s[ord[j]];   // <f, w_k>
+    for (int j = S.first; j != NKA_NIL; j = S.next[j]) {
+      double cj = rhs[j];
+      for (int i = S.first; i != j; i = S.next[i]) cj -= NKA_H(S, j, i) * S.c[i];
+      S.c[j] = cj / NKA_H(S, j, j);
+    }
+    for (int j = S.last; j != NKA_NIL; j = S.prev[j]) {
+      double cj = S.c[j];
+      for (int i = S.last; i != j; i = S.prev[i]) cj -= NKA_H(S, i, j) * S.c[i];
+      S.c[j] = cj / NKA_H(S, j, j);
+    }
+    // correction  f += sum_k c_k (v_k - w_k) = sum_k (c_k / s_k) Z[k]   (:419-424)
+    for (int k = S.first; k != NKA_NIL; k = S.next[k]) {
+      const double coef = S.c[k] / S.s[k];
+      if (has_pair && k == S.first) {
+        B.coef_p = coef;
+      } else {
+        B.zcol[B.nz] = k;
+        B.coef[B.nz] = coef;
+        ++B.nz;
+      }
+    }
+    B.write_f = 1;
+  }
+
+  // Step E: push the new slot, mark pending.  src-C/...c:432-443
+  S.prev[nw] = NKA_NIL;
+  S.next[nw] = S.first;
+  if (S.first == NKA_NIL) S.last = nw;
+  else S.prev[S.first] = nw;
+  S.first = nw;
+  S.pending = 1;
+  S.chained[nw] = 0;
+  ++S.ncalls;
+
+  nka_build_plan_a(S);
+}
+
+// Structural invariant check, src-F08/nka_type.F90:460-524 (0-based).
+NKA_HD int nka_state_defined(const NkaDevState& S)
+{
+  if (S.mvec < 1 || S.mvec + 1 > NKA_MAXSLOT) return 0;
+  if (!(S.vtol > 0.0)) return 0;
+  if (S.error) return 0;
+  const int n = S.mvec + 1;
+  for (int k = 0; k < n; ++k)
+    if (S.next[k] < NKA_NIL || S.next[k] >= n) return 0;
+  if (S.first < NKA_NIL || S.first >= n) return 0;
+  if (S.free_ < NKA_NIL || S.free_ >= n) return 0;
+  bool tag[NKA_MAXSLOT];
+  for (int k = 0; k < n; ++k) tag[k] = false;
+  if (S.first == NKA_NIL) {
+    if (S.last != NKA_NIL) return 0;
+  } else {
+    int k = S.first;
+    if (S.prev[k] != NKA_NIL) return 0;
+    tag[k] = true;
+    while (S.next[k] != NKA_NIL) {
+      if (S.prev[S.next[k]] != k) return 0;
+      k = S.next[k];
+      if (tag[k]) return 0;
+      tag[k] = true;
+    }
+    if (S.last != k) return 0;
+  }
+  for (int k = S.free_; k != NKA_NIL; k = S.next[k]) {
+    if (tag[k]) return 0;
+    tag[k] = true;
+  }
+  for (int k = 0; k < n; ++k)
+    if (!tag[k]) return 0;
+  return 1;
+}

@@ -1,0 +1,291 @@
+"""Parity of the CUDA path against the oracle, through the C-ABI (-m gpu).
+
+Bars (BASELINE.json north_star): every correction vector within 1e-12
+(norm-wise relative) of the reference's accel_update on the same inputs,
+identical drop / eviction / relax decisions (num_vec after every call), and
+the example's Picard iteration count.
+
+Which oracle: the serial-sum port (bit-identical to the compiled reference)
+for n <= 2^18; above that the same algorithm with long-double dot products,
+because the reference's own left-to-right summation noise exceeds 1e-12 there
+(hard part 3).  For the deliberately ill-conditioned stress
+sequences the tolerance is the larger of 1e-12 and 4x the reference's own
+serial-vs-long-double spread on that very call (stated in the assert).
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import scenarios as S
+from oracle import api
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _dev(x):
+    torch = _torch()
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def _rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("name", sorted(S.SCENARIOS))
+def test_scenarios_match_oracle(name):
+    from nka_b200 import NKA
+    n, mvec, vtol, mk = S.SCENARIOS[name]
+    ops = mk()
+    serial, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=0), ops)
+    arbiter, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=1), ops)
+    orc = api.OracleNKA(n, mvec, vtol, dotmode=0)
+    acc = NKA(n, mvec, vtol)
+    it = 0
+    for op in ops:
+        if op[0] == "update":
+            fin = op[1]
+            want = fin.copy()
+            orc.accel_update(want)
+            d = _dev(fin)
+            acc.accel_update(d)
+            got = d.cpu().numpy()
+            st = acc.state()
+            assert st["error"] == 0
+            assert (st["ndrop_last"], bool(st["relaxed_last"]), bool(st["evicted_last"])) == \
+                   (orc.ndrop_last(), orc.relaxed_last(), orc.evicted_last()), (name, it)
+            scale = max(np.linalg.norm(want), np.linalg.norm(fin))
+            noise = np.linalg.norm(serial[it] - arbiter[it])
+            err = np.linalg.norm(got - want)
+            assert err <= max(1e-12 * scale, 4.0 * noise), (name, it, err / scale, noise / scale)
+            it += 1
+        elif op[0] == "relax":
+            orc.relax(); acc.relax()
+        else:
+            orc.restart(); acc.restart()
+        assert acc.num_vec() == orc.num_vec(), (name, it)
+        assert acc.defined()
+    acc.delete()
+
+
+@pytest.mark.parametrize("name", ["iid_n64_m3", "iid_n1000_m10", "odd_n1023_m7", "n4097_m2", "mvec1_n17"])
+def test_well_conditioned_strict_1e12(name):
+    """Strict bar, no noise allowance: ||got - want|| <= 1e-12 ||want|| on every call."""
+    from nka_b200 import NKA
+    n, mvec, vtol, mk = S.SCENARIOS[name]
+    orc = api.OracleNKA(n, mvec, vtol)
+    acc = NKA(n, mvec, vtol)
+    for op in mk():
+        want = op[1].copy()
+        orc.accel_update(want)
+        d = _dev(op[1])
+        acc.accel_update(d)
+        assert _rel(d.cpu().numpy(), want) <= 1e-12
+    acc.delete()
+
+
+def test_host_pointer_drop_in_path():
+    """nka_accel_update(NKA, double*) with a HOST pointer, as a reference caller would pass it."""
+    from nka_b200 import _lib
+    lib = _lib.load()
+    n, mvec, vtol, mk = S.SCENARIOS["iid_n1000_m10"]
+    h = lib.nka_init(n, mvec, vtol, None)
+    orc = api.OracleNKA(n, mvec, vtol)
+    for op in mk():
+        want = op[1].copy()
+        orc.accel_update(want)
+        got = op[1].copy()
+        lib.nka_accel_update(h, got.ctypes.data)      # host memory: staged inside the call
+        assert _rel(got, want) <= 1e-12
+        assert lib.nka_num_vec(h) == orc.num_vec()
+    assert (lib.nka_max_vec(h), lib.nka_vec_len(h), lib.nka_vec_tol(h)) == (mvec, n, vtol)
+    lib.nka_delete(h)
+
+
+def test_device_pointer_autodetected_by_drop_in_entry():
+    from nka_b200 import _lib
+    lib = _lib.load()
+    torch = _torch()
+    n, mvec, vtol, mk = S.SCENARIOS["iid_n64_m3"]
+    h = lib.nka_init(n, mvec, vtol, None)
+    orc = api.OracleNKA(n, mvec, vtol)
+    for op in mk():
+        want = op[1].copy()
+        orc.accel_update(want)
+        d = _dev(op[1])
+        lib.nka_accel_update(h, d.data_ptr())
+        lib.nka_synchronize(h)
+        assert _rel(d.cpu().numpy(), want) <= 1e-12
+    lib.nka_delete(h)
+
+
+def test_unaligned_and_odd_vectors():
+    """f that is only 8-byte aligned takes the scalar-load kernels; odd n exercises the tail."""
+    from nka_b200 import NKA
+    torch = _torch()
+    for n in (1, 2, 3, 255, 256, 257, 1001):
+        mvec = 3
+        rng = np.random.default_rng(n)
+        orc = api.OracleNKA(n, mvec, 0.01, dotmode=1)
+        acc = NKA(n, mvec, 0.01)
+        buf = torch.zeros(n + 1, dtype=torch.float64, device="cuda")
+        for t in range(7):
+            f = rng.uniform(-0.5, 0.5, n)
+            want = f.copy()
+            orc.accel_update(want)
+            view = buf[1:]                      # data_ptr % 16 == 8
+            view.copy_(torch.from_numpy(f))
+            assert view.data_ptr() % 16 == 8
+            acc.accel_update(view)
+            got = view.cpu().numpy()
+            scale = max(np.linalg.norm(want), np.linalg.norm(f))
+            assert np.linalg.norm(got - want) <= 1e-11 * scale, (n, t)   # n <= 3: rank-deficient, drops
+            assert acc.num_vec() == orc.num_vec()
+        acc.delete()
+
+
+def test_empty_vector():
+    from nka_b200 import NKA
+    torch = _torch()
+    acc = NKA(0, 3, 0.01)
+    orc = api.OracleNKA(0, 3, 0.01)
+    f = torch.zeros(0, dtype=torch.float64, device="cuda")
+    for _ in range(5):
+        acc.accel_update(f)
+        orc.accel_update(np.zeros(0))
+        assert acc.num_vec() == orc.num_vec()
+    assert acc.defined()
+
+
+def test_large_n_against_long_double_arbiter():
+    """n = 2^20, mvec = 10: above the range where the serial reference is itself 1e-12-accurate."""
+    from nka_b200 import NKA
+    n, mvec = 1 << 20, 10
+    rng = np.random.default_rng(42)
+    orc = api.OracleNKA(n, mvec, 0.01, dotmode=1)
+    acc = NKA(n, mvec, 0.01)
+    for t in range(14):
+        f = rng.uniform(-0.5, 0.5, n)
+        want = f.copy()
+        orc.accel_update(want)
+        d = _dev(f)
+        acc.accel_update(d)
+        assert _rel(d.cpu().numpy(), want) <= 1e-12, t
+        assert acc.num_vec() == orc.num_vec()
+    acc.delete()
+
+
+def test_example_replay_open_loop():
+    """The example's own 26-call f-sequence (n = 2500, mvec = 5, vtol = 0.01): every correction
+    within 1e-12, num_vec 0,1,2,3,4,5,5,...; pins src-F95/reference_output:5-31 through the oracle."""
+    from nka_b200 import NKA
+    res = api.example_solve(mvec=5, record=True)
+    acc = NKA(2500, 5, 0.01)
+    for t in range(res["iters"]):
+        d = _dev(res["fseq"][t])
+        acc.accel_update(d)
+        assert _rel(d.cpu().numpy(), res["gseq"][t]) <= 1e-12, t
+        assert acc.num_vec() == res["nvec"][t]
+    acc.delete()
+
+
+def _closed_loop(nx, ny, nsweep, mvec, scaling):
+    """The example's Picard loop with the oracle's CPU physics either side of the CUDA accel_update."""
+    from nka_b200 import NKA
+    import ctypes as C
+    lib = api.oracle_lib()
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    sysm = lib.orc_system_init(nx, ny, 0.02, scaling)
+    n = nx * ny
+    upad = np.zeros((ny + 2, nx + 2))
+    r = np.zeros(n)
+    lib.orc_residual(sysm, dp(upad), dp(r))
+    rnorm = [lib.orc_l2norm(dp(r), n)]
+    acc = NKA(n, mvec, 0.01)
+    for itr in range(1, 1000):
+        lib.orc_ssor(sysm, nsweep, 1.4, dp(r))
+        d = _dev(r)
+        acc.accel_update(d)
+        r[:] = d.cpu().numpy()
+        upad[1:-1, 1:-1] -= r.reshape(ny, nx)
+        lib.orc_residual(sysm, dp(upad), dp(r))
+        rnorm.append(lib.orc_l2norm(dp(r), n))
+        if rnorm[-1] < 1e-6 * rnorm[0]:
+            break
+    lib.orc_system_delete(sysm)
+    acc.delete()
+    return np.array(rnorm)
+
+
+def test_example_closed_loop_identical_iteration_count_and_table():
+    """Identical Picard iteration count (26) and a residual table equal, line for line, to the
+    reference's golden output (7 significant digits)."""
+    rn = _closed_loop(50, 50, 2, 5, scaling=0)
+    with open(os.path.join(os.path.dirname(__file__), "golden", "example_c_f95.txt")) as fh:
+        text = fh.read().split("UNACCELERATED SOLVE")[0]
+    want = [ln for ln in text.splitlines() if ":" in ln[:4] and ln[:3].strip().isdigit()]
+    assert len(rn) - 1 == 26
+    assert api.format_table(rn) == want
+
+
+def test_example_closed_loop_f08_four_sweeps():
+    """src-F08/reference_output:25: --sweeps 4 --nka-vec 5 -> 20 iterations, 4.652602E-05."""
+    rn = _closed_loop(50, 50, 4, 5, scaling=1)
+    assert api.format_table(rn)[-1] == " 20:  4.652602E-05    9.305E-07   0.499"
+
+
+def test_queries_relax_restart_set_vec_tol():
+    from nka_b200 import NKA
+    n = 300
+    acc = NKA(n, 4, 0.02)
+    assert (acc.vec_len(), acc.max_vec(), acc.vec_tol(), acc.num_vec()) == (n, 4, 0.02, 0)
+    acc.set_vec_tol(0.3)
+    assert acc.vec_tol() == 0.3 and acc.state()["vtol"] == 0.3
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        acc.accel_update(_dev(rng.uniform(-1, 1, n)))
+    assert acc.num_vec() == 2
+    acc.relax(); acc.relax()
+    assert acc.num_vec() == 2 and acc.state()["pending"] == 0
+    acc.restart()
+    assert acc.num_vec() == 0 and acc.defined()
+    acc.init(10, 2)                      # re-init frees and reallocates (intent(out))
+    assert acc.vec_len() == 10 and acc.max_vec() == 2
+    acc.delete()
+    assert not acc.defined()
+
+
+def test_deterministic_bitwise_rerun():
+    """Fixed-order reductions: two runs on the same inputs agree bit for bit."""
+    from nka_b200 import NKA
+    n, mvec = 200003, 6
+    outs = []
+    for _ in range(2):
+        rng = np.random.default_rng(9)
+        acc = NKA(n, mvec, 0.01)
+        run = []
+        for t in range(10):
+            d = _dev(rng.uniform(-0.5, 0.5, n))
+            acc.accel_update(d)
+            run.append(d.cpu().numpy())
+        outs.append(run)
+        acc.delete()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
+def test_abort_with_file_line_on_violated_precondition():
+    """The C library keeps the reference's ASSERT convention: message with file:line, then abort."""
+    code = ("import sys; sys.path.insert(0, %r); from nka_b200 import _lib; L = _lib.load(); "
+            "L.nka_init(10, 0, 0.01, None)" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert r.returncode != 0
+    assert "nka_capi.cu" in r.stderr and "mvec must be > 0" in r.stderr

@@ -1,0 +1,65 @@
+"""CPU check of the device algorithm's scalar half.
+
+tests/model/ compiles nka_b200/csrc/nka_state.h -- the exact code the state
+kernel runs on the device -- for the host, with plain-loop stand-ins for the
+streaming kernels.  Run against the oracle this pins the raw-chain storage
+scheme, the materialisation rule, the drop/evict/relax decisions and the host
+bookkeeping (pending flag, list-length bound) without a GPU.  The product
+never uses this model; the -m gpu tests check the real kernels.
+"""
+import numpy as np
+import pytest
+
+import scenarios as S
+from model import ModelNKA
+from oracle import api
+
+
+def _noise_floor(n, mvec, vtol, ops):
+    """The reference's own sensitivity: serial-sum vs long-double-sum runs of the same code."""
+    a, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=0), ops)
+    b, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=1), ops)
+    return a, b
+
+
+@pytest.mark.parametrize("name", sorted(S.SCENARIOS))
+def test_model_matches_oracle(name):
+    n, mvec, vtol, mk = S.SCENARIOS[name]
+    ops = mk()
+    serial, arbiter = _noise_floor(n, mvec, vtol, ops)
+    orc = api.OracleNKA(n, mvec, vtol, dotmode=1)
+    mod = ModelNKA(n, mvec, vtol)
+    it = 0
+    for op in ops:
+        if op[0] == "update":
+            fin = op[1]
+            a, b = fin.copy(), fin.copy()
+            orc.accel_update(a)
+            mod.accel_update(b)
+            assert (orc.ndrop_last(), orc.relaxed_last(), orc.evicted_last()) == \
+                   (mod.ndrop_last(), bool(mod.relaxed_last()), bool(mod.evicted_last()))
+            scale = max(np.linalg.norm(a), np.linalg.norm(fin))
+            noise = np.linalg.norm(serial[it] - arbiter[it])
+            assert np.linalg.norm(a - b) <= max(1e-12 * scale, 4.0 * noise), (name, it)
+            it += 1
+        elif op[0] == "relax":
+            orc.relax(); mod.relax()
+        else:
+            orc.restart(); mod.restart()
+        assert orc.num_vec() == mod.num_vec()
+        assert mod.defined() and mod.error() == 0
+        assert mod.host_pending() == mod.dev_pending()
+        assert mod.list_len() <= mod.ub_len()
+    assert mod.bound_violations() == 0
+
+
+def test_model_materialises_only_on_breaks():
+    """No vtol drop, no relax, no s == 0: the chain is never materialised."""
+    n, mvec, vtol, mk = S.SCENARIOS["iid_n1000_m10"]
+    mod = ModelNKA(n, mvec, vtol)
+    S.run_ops(mod, mk())
+    assert mod.mat_entries() == 0
+    n, mvec, vtol, mk = S.SCENARIOS["relax_restart_n96_m4"]
+    mod = ModelNKA(n, mvec, vtol)
+    S.run_ops(mod, mk())
+    assert mod.mat_entries() > 0
