@@ -26,8 +26,9 @@ extern "C" {
 
 /* nka_init with a 64-bit length (the reference's int arithmetic overflows at
  * (mvec+1)*vlen >= 2^31, src-C/nonlinear_krylov_accelerator.c:235,241).
- * device < 0: the current CUDA device.  stream: a cudaStream_t, or NULL for a
- * stream owned by the handle.  Fortran: init, src-F08/nka_type.F90:185-200
+ * device < 0: the current CUDA device.  stream: a cudaStream_t, or NULL for the
+ * legacy default stream (work is then ordered after whatever the caller queued
+ * there, as with the synchronous CPU interface this replaces).  Fortran: init, src-F08/nka_type.F90:185-200
  * (vtol defaults to 0.01 there, :160). */
 NKA nka_init_ex (size_t vlen, int mvec, double vtol, int device, void *stream);
 

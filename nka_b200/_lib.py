@@ -71,9 +71,11 @@ def load() -> C.CDLL:
     """Return the loaded library; build it first if the tree has none."""
     global _lib
     if _lib is None:
-        path = _build.LIB_PATH
-        if not os.path.exists(path):
-            path = _build.build_library()
+        path = os.environ.get("NKA_B200_LIB")      # tuning builds only (tools/tune.py)
+        if not path:
+            path = _build.LIB_PATH
+            if not os.path.exists(path):
+                path = _build.build_library()
         lib = C.CDLL(path)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(lib, name)      # AttributeError if the ABI drifted: loud by design

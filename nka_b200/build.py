@@ -60,6 +60,21 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+def build_variant(tag: str, defines: dict, instantiate_max: int = 11) -> str:
+    """Tuning builds (tools/tune.py): the same sources with -D overrides, written next to
+    the product library as lib/variants/libnka_b200_<tag>.so.  Never loaded by default."""
+    vdir = os.path.join(LIB_DIR, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, "libnka_b200_%s.so" % tag)
+    nvcc = os.environ.get("NVCC", "nvcc")
+    dflags = ["-D%s=%s" % kv for kv in defines.items()] + ["-DNKA_INSTANTIATE_MAX=%d" % instantiate_max]
+    cmd = [nvcc, *NVCC_FLAGS, *dflags, "-shared", "-o", out, *sources(), "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed: %s\n%s%s" % (" ".join(cmd), r.stdout, r.stderr))
+    return out
+
+
 if __name__ == "__main__":
     import sys
     print(build_library(force=True, verbose="-v" in sys.argv))

@@ -53,10 +53,19 @@ template <int N> struct FillTables {
 };
 template <> struct FillTables<0> { static void run() {} };
 
+#ifndef NKA_INSTANTIATE_MAX
+#define NKA_INSTANTIATE_MAX NKA_MAXSLOT     // tuning builds instantiate fewer sizes to compile faster
+#endif
 static bool g_tables_ready = false;
+static int g_grid_per_sm_a = 0, g_grid_per_sm_b = 0;   // 0 = occupancy-derived; env overrides for tuning
 static void ensure_tables()
 {
-  if (!g_tables_ready) { FillTables<NKA_MAXSLOT>::run(); g_tables_ready = true; }
+  if (!g_tables_ready) {
+    FillTables<NKA_INSTANTIATE_MAX>::run();
+    if (const char* e = getenv("NKA_GRID_PER_SM_A")) g_grid_per_sm_a = atoi(e);
+    if (const char* e = getenv("NKA_GRID_PER_SM_B")) g_grid_per_sm_b = atoi(e);
+    g_tables_ready = true;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -195,8 +204,9 @@ static int occupancy_a(NKA st, int nc, int V)
 {
   if (st->occ_a[nc][V] < 0) {
     int nb = 0;
+    NKA_REQUIRE(g_pass_a[nc][V] != nullptr, "pass A is not instantiated for this subspace size in this build");
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_pass_a[nc][V], NKA_THREADS, 0));
-    st->occ_a[nc][V] = nb;
+    st->occ_a[nc][V] = g_grid_per_sm_a > 0 ? g_grid_per_sm_a : nb;
   }
   return st->occ_a[nc][V];
 }
@@ -205,8 +215,9 @@ static int occupancy_b(NKA st, int nz, int V)
 {
   if (st->occ_b[nz][V] < 0) {
     int nb = 0;
+    NKA_REQUIRE(g_pass_b[nz][V] != nullptr, "pass B is not instantiated for this subspace size in this build");
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_pass_b[nz][V], NKA_THREADS, 0));
-    st->occ_b[nz][V] = nb;
+    st->occ_b[nz][V] = g_grid_per_sm_b > 0 ? g_grid_per_sm_b : nb;
   }
   return st->occ_b[nz][V];
 }
@@ -246,8 +257,10 @@ extern "C" NKA nka_init_ex(size_t vlen, int mvec, double vtol, int device, void*
   st->vtol = vtol;
   st->ld = ((vlen + 15) / 16) * 16;                 // 128-byte aligned columns
   if (st->ld == 0) st->ld = 16;
-  if (stream) { st->stream = (cudaStream_t)stream; st->own_stream = false; }
-  else { CUDA_CHECK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking)); st->own_stream = true; }
+  // NULL = the legacy default stream: ordered after everything the caller queued on it
+  // (and on other blocking streams), like the synchronous CPU interface it replaces
+  st->stream = (cudaStream_t)stream;
+  st->own_stream = false;
   for (int i = 0; i <= NKA_MAXSLOT; ++i)
     for (int v = 0; v < 3; ++v) { st->occ_a[i][v] = -1; st->occ_b[i][v] = -1; }
 
@@ -261,7 +274,7 @@ extern "C" NKA nka_init_ex(size_t vlen, int mvec, double vtol, int device, void*
              poolbytes, cudaGetErrorString(e));
     nka_fail(__FILE__, __LINE__, b);
   }
-  st->max_grid = st->num_sms * 8;
+  st->max_grid = st->num_sms * 16;
   CUDA_CHECK(cudaMalloc(&st->S, sizeof(NkaDevState)));
   CUDA_CHECK(cudaMalloc(&st->dots, 2 * NKA_MAXSLOT * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&st->partials, (size_t)st->max_grid * 2 * NKA_MAXSLOT * sizeof(double)));
@@ -327,7 +340,7 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
   }
   {
     SpanScope t(st, T_STATE);
-    nka_state_kernel<<<1, 32, 0, st->stream>>>(st->S, st->dots);
+    nka_state_kernel<<<1, NKA_STATE_THREADS, 0, st->stream>>>(st->S, st->dots);
     CUDA_CHECK(cudaGetLastError());
     st->launches += 1;
   }
@@ -379,7 +392,7 @@ extern "C" void nka_restart(NKA st)
 {
   NKA_REQUIRE(st != NULL, "nka_restart: null handle");
   DeviceGuard guard(st->device);
-  nka_restart_kernel<<<1, 32, 0, st->stream>>>(st->S);
+  nka_restart_kernel<<<1, NKA_STATE_THREADS, 0, st->stream>>>(st->S);
   CUDA_CHECK(cudaGetLastError());
   st->launches += 1;
   st->pending = false;
@@ -391,7 +404,7 @@ extern "C" void nka_relax(NKA st)
   NKA_REQUIRE(st != NULL, "nka_relax: null handle");
   if (!st->pending) return;                       // src-C/...c:470: nothing pending, nothing to do
   DeviceGuard guard(st->device);
-  nka_relax_kernel<<<1, 32, 0, st->stream>>>(st->S);
+  nka_relax_kernel<<<1, NKA_STATE_THREADS, 0, st->stream>>>(st->S);
   CUDA_CHECK(cudaGetLastError());
   st->launches += 1;
   if (st->ub_len >= 2) {
@@ -474,9 +487,7 @@ extern "C" void nka_set_stream(NKA st, void* stream)
   DeviceGuard guard(st->device);
   fold_timing(st);
   CUDA_CHECK(cudaStreamSynchronize(st->stream));
-  if (st->own_stream) { cudaStreamDestroy(st->stream); st->own_stream = false; }
-  if (stream) st->stream = (cudaStream_t)stream;
-  else { CUDA_CHECK(cudaStreamCreateWithFlags(&st->stream, cudaStreamNonBlocking)); st->own_stream = true; }
+  st->stream = (cudaStream_t)stream;
 }
 
 extern "C" void* nka_get_stream(NKA st) { NKA_REQUIRE(st != NULL, "nka_get_stream: null handle"); return (void*)st->stream; }

@@ -20,7 +20,17 @@
 
 #include "nka_state.h"
 
+// Tunables (profiles/ records the sweep that picked the defaults).
+#ifndef NKA_THREADS
 #define NKA_THREADS 256
+#endif
+#ifndef NKA_MINB_A
+#define NKA_MINB_A 1      // __launch_bounds__ min CTAs/SM for pass A (2 caps it at 128 registers)
+#endif
+#ifndef NKA_MINB_B
+#define NKA_MINB_B 1
+#endif
+#define NKA_STATE_THREADS 128
 
 // ---------------------------------------------------------------------------
 // 16-byte / 8-byte element access with streaming cache hints.  V = 2 uses
@@ -105,7 +115,7 @@ __device__ __forceinline__ void nka_pass_a_elem(const double* __restrict__ f, co
 }
 
 template <int NC, int V>
-__global__ void __launch_bounds__(NKA_THREADS)
+__global__ void __launch_bounds__(NKA_THREADS, NKA_MINB_A)
 nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld, size_t n,
            const NkaDevState* __restrict__ S, double* __restrict__ partials, unsigned* __restrict__ ticket,
            double* __restrict__ dots)
@@ -168,21 +178,56 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
 }
 
 // ---------------------------------------------------------------------------
-// State kernel: one thread runs the scalar algorithm.
+// State kernels.  The ~10 KB state is staged through shared memory: the scalar
+// algorithm is a chain of dependent loads, and from global memory every one of
+// them paid an L2 round trip (43 us at mvec = 10 on B200; see profiles/).
 // ---------------------------------------------------------------------------
-__global__ void nka_state_kernel(NkaDevState* S, const double* dots)
+struct NkaStateStage {
+  NkaDevState st;
+  double dots[2 * NKA_MAXSLOT];
+};
+
+__device__ __forceinline__ void nka_stage_in(NkaStateStage& sm, const NkaDevState* S, const double* dots)
 {
-  if (threadIdx.x == 0 && blockIdx.x == 0) nka_state_step(*S, dots, NKA_MAXSLOT);
+  static_assert(sizeof(NkaDevState) % 4 == 0, "state is copied in 4-byte words");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(S);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.st);
+  for (unsigned i = threadIdx.x; i < sizeof(NkaDevState) / 4; i += blockDim.x) dst[i] = __ldcg(src + i);
+  if (dots)
+    for (unsigned i = threadIdx.x; i < 2 * NKA_MAXSLOT; i += blockDim.x) sm.dots[i] = __ldcg(dots + i);
+  __syncthreads();
 }
 
-__global__ void nka_relax_kernel(NkaDevState* S)
+__device__ __forceinline__ void nka_stage_out(const NkaStateStage& sm, NkaDevState* S)
 {
-  if (threadIdx.x == 0 && blockIdx.x == 0) nka_state_relax(*S);
+  __syncthreads();
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.st);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(S);
+  for (unsigned i = threadIdx.x; i < sizeof(NkaDevState) / 4; i += blockDim.x) dst[i] = src[i];
 }
 
-__global__ void nka_restart_kernel(NkaDevState* S)
+__global__ void __launch_bounds__(NKA_STATE_THREADS) nka_state_kernel(NkaDevState* S, const double* dots)
 {
-  if (threadIdx.x == 0 && blockIdx.x == 0) nka_state_restart(*S);
+  __shared__ NkaStateStage sm;
+  nka_stage_in(sm, S, dots);
+  if (threadIdx.x == 0) nka_state_step(sm.st, sm.dots, NKA_MAXSLOT);
+  nka_stage_out(sm, S);
+}
+
+__global__ void __launch_bounds__(NKA_STATE_THREADS) nka_relax_kernel(NkaDevState* S)
+{
+  __shared__ NkaStateStage sm;
+  nka_stage_in(sm, S, nullptr);
+  if (threadIdx.x == 0) nka_state_relax(sm.st);
+  nka_stage_out(sm, S);
+}
+
+__global__ void __launch_bounds__(NKA_STATE_THREADS) nka_restart_kernel(NkaDevState* S)
+{
+  __shared__ NkaStateStage sm;
+  nka_stage_in(sm, S, nullptr);
+  if (threadIdx.x == 0) nka_state_restart(sm.st);
+  nka_stage_out(sm, S);
 }
 
 __global__ void nka_init_kernel(NkaDevState* S, int mvec, double vtol)
@@ -255,7 +300,7 @@ __device__ __forceinline__ void nka_pass_b_elem(double* __restrict__ f, double* 
 }
 
 template <int NZ, int V>
-__global__ void __launch_bounds__(NKA_THREADS)
+__global__ void __launch_bounds__(NKA_THREADS, NKA_MINB_B)
 nka_pass_b(double* __restrict__ f, double* __restrict__ W, double* __restrict__ Z, size_t ld, size_t n,
            const NkaDevState* __restrict__ S)
 {

@@ -162,3 +162,19 @@ def run_ops(acc, ops):
             acc.restart()
         nvecs.append(acc.num_vec())
     return outs, nvecs
+
+
+def tolerances(serial, arbiter, inputs, factor=10.0):
+    """Per-call relative tolerance for comparing an implementation with the long-double
+    arbiter: 1e-12, or `factor` times the reference's OWN sensitivity to summation order
+    (its serial-sum run vs its long-double-sum run, same code) if that is larger.  The
+    sensitivity is carried forward as a running maximum because a perturbed stored
+    vector keeps influencing later calls.  Returns (scales, rel_tols)."""
+    scales, tols = [], []
+    worst = 0.0
+    for a, b, fin in zip(serial, arbiter, inputs):
+        scale = max(np.linalg.norm(b), np.linalg.norm(fin), 1e-300)
+        worst = max(worst, np.linalg.norm(a - b) / scale)
+        scales.append(scale)
+        tols.append(max(1e-12, factor * worst))
+    return scales, tols

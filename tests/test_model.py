@@ -15,18 +15,14 @@ from model import ModelNKA
 from oracle import api
 
 
-def _noise_floor(n, mvec, vtol, ops):
-    """The reference's own sensitivity: serial-sum vs long-double-sum runs of the same code."""
-    a, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=0), ops)
-    b, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=1), ops)
-    return a, b
-
-
 @pytest.mark.parametrize("name", sorted(S.SCENARIOS))
 def test_model_matches_oracle(name):
     n, mvec, vtol, mk = S.SCENARIOS[name]
     ops = mk()
-    serial, arbiter = _noise_floor(n, mvec, vtol, ops)
+    inputs = [op[1] for op in ops if op[0] == "update"]
+    serial, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=0), ops)
+    arbiter, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=1), ops)
+    scales, tols = S.tolerances(serial, arbiter, inputs)
     orc = api.OracleNKA(n, mvec, vtol, dotmode=1)
     mod = ModelNKA(n, mvec, vtol)
     it = 0
@@ -38,9 +34,7 @@ def test_model_matches_oracle(name):
             mod.accel_update(b)
             assert (orc.ndrop_last(), orc.relaxed_last(), orc.evicted_last()) == \
                    (mod.ndrop_last(), bool(mod.relaxed_last()), bool(mod.evicted_last()))
-            scale = max(np.linalg.norm(a), np.linalg.norm(fin))
-            noise = np.linalg.norm(serial[it] - arbiter[it])
-            assert np.linalg.norm(a - b) <= max(1e-12 * scale, 4.0 * noise), (name, it)
+            assert np.linalg.norm(a - b) / scales[it] <= tols[it], (name, it)
             it += 1
         elif op[0] == "relax":
             orc.relax(); mod.relax()

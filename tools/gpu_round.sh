@@ -1,0 +1,39 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, bench, ncu launch list + full capture, tuning sweep.
+# Usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag> [tests] [bench] [ncu] [tune]
+tag=$1; shift
+mkdir -p gpurun_out
+for what in "$@"; do
+case $what in
+tests)
+  timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest_rc=$?" >> gpurun_out/pytest_gpu_$tag.log
+  tail -4 gpurun_out/pytest_gpu_$tag.log
+  timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$tag.log 2>&1; echo "smoke_rc=$?" >> gpurun_out/smoke_$tag.log
+  tail -2 gpurun_out/smoke_$tag.log ;;
+bench)
+  timeout 900 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err; echo "bench_rc=$?"
+  cut -c1-400 gpurun_out/bench_$tag.json; tail -3 gpurun_out/bench_$tag.err ;;
+ncu)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$tag.csv \
+     python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_list_$tag.log 2>&1
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:nka_pass -s 34 -c 4 -f -o gpurun_out/prof_$tag \
+     python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_$tag.log 2>&1
+  ls -la gpurun_out/prof_$tag.ncu-rep ;;
+tune)
+  : > gpurun_out/tune_$tag.jsonl
+  for lib in default t256_b2 t256_b3 t512_b1 t128_b4 t128_b3; do
+    for g in 0 1 2 3 4 6 8; do
+      if [ $lib = default ]; then unset NKA_B200_LIB; else export NKA_B200_LIB=$PWD/nka_b200/lib/variants/libnka_b200_$lib.so; fi
+      if [ $g = 0 ]; then unset NKA_GRID_PER_SM_A NKA_GRID_PER_SM_B; else export NKA_GRID_PER_SM_A=$g NKA_GRID_PER_SM_B=$g; fi
+      TUNE_TAG="$lib/g$g" timeout 120 python tools/tune.py >> gpurun_out/tune_$tag.jsonl 2>> gpurun_out/tune_$tag.err
+    done
+  done
+  unset NKA_B200_LIB NKA_GRID_PER_SM_A NKA_GRID_PER_SM_B
+  python - <<PY
+import json
+for ln in open("gpurun_out/tune_$tag.jsonl"):
+    d=json.loads(ln); print("%-14s grid=%s upd=%.3fms A=%.3f (%.0f GB/s) B=%.3f (%.0f GB/s) state=%.3f frac=%.3f"%(d["tag"],(d["grid"]["grid_a"],d["grid"]["grid_b"]),d["ms_update"],d["ms_a"],d["tbs_a_actual"],d["ms_b"],d["tbs_b_actual"],d["ms_state"],d["frac_roofline"]))
+PY
+  ;;
+esac
+done

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Kernel tuning sweep (run on the GPU box): times pass A / pass B in steady state for the
+library named by $NKA_B200_LIB (default: the product build) and the grid overrides in
+$NKA_GRID_PER_SM_A / _B.  Prints one JSON line.  Not part of the product."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import torch  # noqa: E402
+
+from nka_b200 import NKA  # noqa: E402
+
+
+def main():
+    n = int(os.environ.get("TUNE_N", str(1 << 28)))
+    m = int(os.environ.get("TUNE_M", "10"))
+    steps = int(os.environ.get("TUNE_STEPS", "30"))
+    acc = NKA(n, m, 0.01)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    pool = [torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) - 0.5 for _ in range(m + 3)]
+    k = 0
+    for _ in range(m + 5):
+        acc.accel_update(pool[k % len(pool)]); k += 1
+    acc.synchronize()
+    acc.timing_enable(True)
+    acc.timing_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        acc.accel_update(pool[k % len(pool)]); k += 1
+    e1.record()
+    torch.cuda.synchronize()
+    t = acc.timing_read()
+    total = e0.elapsed_time(e1) / steps
+    a = t["pass_a"]["ms"] / steps
+    b = t["pass_b"]["ms"] / steps
+    out = {
+        "tag": os.environ.get("TUNE_TAG", "default"), "n": n, "m": m,
+        "grid": acc.launch_geometry(), "ms_update": total, "ms_a": a, "ms_b": b,
+        "ms_state": t["state"]["ms"] / steps, "ms_mat": t["materialise"]["ms"] / max(t["materialise"]["count"], 1),
+        "tbs_a_actual": (m + 2) * n * 8 / a / 1e9, "tbs_b_actual": (m + 5) * n * 8 / b / 1e9,
+        "updates_per_s": 1e3 / total, "frac_roofline": (2 * m + 4) * n * 8 / (total * 1e-3) / 1e9 / 6554.9,
+        "num_vec": acc.num_vec(),
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
