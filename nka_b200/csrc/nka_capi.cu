@@ -15,7 +15,8 @@
 #include <vector>
 
 #include "../../include/nka_b200.h"
-#include "nka_kernels.cuh"
+#include "nka_dispatch.h"
+#include "nka_aux_kernels.cuh"
 
 #define NKA_VERSION "nka_b200 0.1 (sm_100a)"
 
@@ -34,34 +35,13 @@
     nka_fail(__FILE__, __LINE__, b_); } } while (0)
 
 // ---------------------------------------------------------------------------
-// kernel dispatch tables
+// kernel dispatch (tables live in nka_pass_a.cu / nka_pass_b.cu)
 // ---------------------------------------------------------------------------
-typedef void (*PassAFn)(const double*, const double*, size_t, size_t, const NkaDevState*, double*, unsigned*, double*);
-typedef void (*PassBFn)(double*, double*, double*, size_t, size_t, const NkaDevState*);
-
-static PassAFn g_pass_a[NKA_MAXSLOT + 1][3];   // [NC][V]
-static PassBFn g_pass_b[NKA_MAXSLOT + 1][3];   // [NZ][V]
-
-template <int N> struct FillTables {
-  static void run() {
-    g_pass_a[N][1] = nka_pass_a<N, 1>;
-    g_pass_a[N][2] = nka_pass_a<N, 2>;
-    g_pass_b[N - 1][1] = nka_pass_b<N - 1, 1>;
-    g_pass_b[N - 1][2] = nka_pass_b<N - 1, 2>;
-    FillTables<N - 1>::run();
-  }
-};
-template <> struct FillTables<0> { static void run() {} };
-
-#ifndef NKA_INSTANTIATE_MAX
-#define NKA_INSTANTIATE_MAX NKA_MAXSLOT     // tuning builds instantiate fewer sizes to compile faster
-#endif
 static bool g_tables_ready = false;
 static int g_grid_per_sm_a = 0, g_grid_per_sm_b = 0;   // 0 = occupancy-derived; env overrides for tuning
 static void ensure_tables()
 {
   if (!g_tables_ready) {
-    FillTables<NKA_INSTANTIATE_MAX>::run();
     if (const char* e = getenv("NKA_GRID_PER_SM_A")) g_grid_per_sm_a = atoi(e);
     if (const char* e = getenv("NKA_GRID_PER_SM_B")) g_grid_per_sm_b = atoi(e);
     g_tables_ready = true;
@@ -127,6 +107,7 @@ struct nka_state {
   // host-side knowledge of the device list: exact `pending`, upper bound on its length
   bool pending = false;
   int ub_len = 0;
+  bool lazy = true;             // skip the doomed oldest column in pass A (single GPU only)
   // distributed
   void* comm = nullptr;
   bool own_comm = false;
@@ -204,8 +185,8 @@ static int occupancy_a(NKA st, int nc, int V)
 {
   if (st->occ_a[nc][V] < 0) {
     int nb = 0;
-    NKA_REQUIRE(g_pass_a[nc][V] != nullptr, "pass A is not instantiated for this subspace size in this build");
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_pass_a[nc][V], NKA_THREADS, 0));
+    NKA_REQUIRE(nka_get_pass_a(nc, V) != nullptr, "pass A is not instantiated for this subspace size in this build");
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nka_get_pass_a(nc, V), NKA_THREADS, 0));
     st->occ_a[nc][V] = g_grid_per_sm_a > 0 ? g_grid_per_sm_a : nb;
   }
   return st->occ_a[nc][V];
@@ -215,21 +196,19 @@ static int occupancy_b(NKA st, int nz, int V)
 {
   if (st->occ_b[nz][V] < 0) {
     int nb = 0;
-    NKA_REQUIRE(g_pass_b[nz][V] != nullptr, "pass B is not instantiated for this subspace size in this build");
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_pass_b[nz][V], NKA_THREADS, 0));
+    NKA_REQUIRE(nka_get_pass_b(nz, V) != nullptr, "pass B is not instantiated for this subspace size in this build");
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nka_get_pass_b(nz, V), NKA_THREADS, 0));
     st->occ_b[nz][V] = g_grid_per_sm_b > 0 ? g_grid_per_sm_b : nb;
   }
   return st->occ_b[nz][V];
 }
 
-// How many older Z columns pass B is expected to keep: exact unless a vtol drop
-// or the s == 0 guard fires on the device (pass B copes with any actual count).
+// How many pairs are expected on the list at entry (pass B streams their Z columns): exact
+// unless a vtol drop fired earlier on the device (pass B copes with any actual count).
 static int nz_expected(NKA st)
 {
-  int nz;
-  if (st->pending) nz = st->ub_len - 1 < st->mvec - 1 ? st->ub_len - 1 : st->mvec - 1;
-  else nz = st->ub_len;
-  return nz < 0 ? 0 : nz;
+  const int nz = st->pending ? st->ub_len - 1 : st->ub_len;
+  return nz < 0 ? 0 : (nz > st->mvec ? st->mvec : nz);
 }
 
 // ---------------------------------------------------------------------------
@@ -263,6 +242,7 @@ extern "C" NKA nka_init_ex(size_t vlen, int mvec, double vtol, int device, void*
   st->own_stream = false;
   for (int i = 0; i <= NKA_MAXSLOT; ++i)
     for (int v = 0; v < 3; ++v) { st->occ_a[i][v] = -1; st->occ_b[i][v] = -1; }
+  if (const char* e = getenv("NKA_LAZY_LAST")) st->lazy = atoi(e) != 0;      // ablation switch
 
   const size_t colbytes = st->ld * sizeof(double);
   const size_t poolbytes = colbytes * (size_t)(mvec + 1);
@@ -281,12 +261,20 @@ extern "C" NKA nka_init_ex(size_t vlen, int mvec, double vtol, int device, void*
   CUDA_CHECK(cudaMalloc(&st->ticket, sizeof(unsigned)));
   CUDA_CHECK(cudaMemsetAsync(st->ticket, 0, sizeof(unsigned), st->stream));
   CUDA_CHECK(cudaMemsetAsync(st->dots, 0, 2 * NKA_MAXSLOT * sizeof(double), st->stream));
-  nka_init_kernel<<<1, 32, 0, st->stream>>>(st->S, mvec, vtol);
+  nka_init_kernel<<<1, 32, 0, st->stream>>>(st->S, mvec, vtol, st->lazy ? 1 : 0);
   CUDA_CHECK(cudaGetLastError());
   st->launches += 1;
   st->pending = false;
   st->ub_len = 0;
   return st;
+}
+
+static void set_lazy(NKA st, bool on)
+{
+  st->lazy = on;
+  nka_set_lazy_kernel<<<1, 32, 0, st->stream>>>(st->S, on ? 1 : 0);
+  CUDA_CHECK(cudaGetLastError());
+  st->launches += 1;
 }
 
 extern "C" NKA nka_init(int vlen, int mvec, double vtol, double (*dp)(int, double*, double*))
@@ -322,33 +310,42 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
   DeviceGuard guard(st->device);
   const size_t n = st->vlen;
   const int V = (((uintptr_t)f) % 16 == 0) ? 2 : 1;
-  const int L = st->ub_len;
+  const int L = st->ub_len;                         // upper bound on the list length at entry
+  const bool single = (st->comm == nullptr);        // single GPU: fused state step, lazy last column
+  const bool may_skip = single && st->lazy && st->pending && L == st->mvec + 1;
+  const int NC = may_skip ? st->mvec : L;           // columns pass A can be asked to stream
 
   if (L > 0) {
-    const int grid = grid_for(st, occupancy_a(st, L, V), n, V);
+    const int grid = grid_for(st, occupancy_a(st, NC, V), n, V);
     {
       SpanScope t(st, T_PASS_A);
-      g_pass_a[L][V]<<<grid, NKA_THREADS, 0, st->stream>>>(f, st->W, st->ld, n, st->S, st->partials, st->ticket, st->dots);
+      nka_get_pass_a(NC, V)<<<grid, NKA_THREADS, 0, st->stream>>>(f, st->W, st->ld, n, st->S, st->partials, st->ticket,
+                                                            st->dots, single ? 1 : 0);
       CUDA_CHECK(cudaGetLastError());
       st->launches += 1;
     }
-    if (st->comm) {
-      SpanScope t(st, T_COMM);
-      const int rc = g_nccl.AllReduce(st->dots, st->dots, 2 * NKA_MAXSLOT, kNcclFloat64, kNcclSum, st->comm, st->stream);
-      if (rc != 0) nka_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclAllReduce failed");
+    if (!single) {
+      {
+        SpanScope t(st, T_COMM);
+        const int rc = g_nccl.AllReduce(st->dots, st->dots, 2 * NKA_MAXSLOT, kNcclFloat64, kNcclSum, st->comm, st->stream);
+        if (rc != 0) nka_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclAllReduce failed");
+      }
+      SpanScope t(st, T_STATE);
+      nka_state_kernel<<<1, NKA_STATE_THREADS, 0, st->stream>>>(st->S, st->dots, 1);
+      CUDA_CHECK(cudaGetLastError());
+      st->launches += 1;
+    } else if (may_skip) {
+      // the oldest column was left out of pass A; this exits at once unless a vtol drop
+      // (or the s == 0 guard) means it is needed after all
+      SpanScope t(st, T_STATE);
+      nka_fixup_kernel<<<grid_for(st, 4, n, 1), NKA_THREADS, 0, st->stream>>>(f, st->W, st->ld, n, st->S, st->partials,
+                                                                             st->ticket, st->dots);
+      CUDA_CHECK(cudaGetLastError());
+      st->launches += 1;
     }
-  }
-  {
+  } else {
     SpanScope t(st, T_STATE);
-    nka_state_kernel<<<1, NKA_STATE_THREADS, 0, st->stream>>>(st->S, st->dots);
-    CUDA_CHECK(cudaGetLastError());
-    st->launches += 1;
-  }
-  if (L >= 2) {
-    // a vtol drop or the s == 0 guard may have broken a chain; the kernel exits at once otherwise
-    SpanScope t(st, T_MAT);
-    const int grid = grid_for(st, 4, n, 1);
-    nka_materialise<<<grid, NKA_THREADS, 0, st->stream>>>(st->W, st->ld, n, st->S);
+    nka_state_kernel<<<1, NKA_STATE_THREADS, 0, st->stream>>>(st->S, st->dots, 1);
     CUDA_CHECK(cudaGetLastError());
     st->launches += 1;
   }
@@ -356,7 +353,7 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
     const int nz = nz_expected(st);
     const int grid = grid_for(st, occupancy_b(st, nz, V), n, V);
     SpanScope t(st, T_PASS_B);
-    g_pass_b[nz][V]<<<grid, NKA_THREADS, 0, st->stream>>>(f, st->W, st->Z, st->ld, n, st->S);
+    nka_get_pass_b(nz, V)<<<grid, NKA_THREADS, 0, st->stream>>>(f, st->W, st->Z, st->ld, n, st->S);
     CUDA_CHECK(cudaGetLastError());
     st->launches += 1;
   }
@@ -530,7 +527,9 @@ extern "C" void nka_launch_geometry(NKA st, int* grid_a, int* grid_b, int* threa
   NKA_REQUIRE(st != NULL, "nka_launch_geometry: null handle");
   DeviceGuard guard(st->device);
   const int L = st->ub_len;
-  if (grid_a) *grid_a = L > 0 ? grid_for(st, occupancy_a(st, L, 2), st->vlen, 2) : 0;
+  const bool may_skip = st->comm == nullptr && st->lazy && st->pending && L == st->mvec + 1;
+  const int NC = may_skip ? st->mvec : L;
+  if (grid_a) *grid_a = L > 0 ? grid_for(st, occupancy_a(st, NC, 2), st->vlen, 2) : 0;
   const int nz = nz_expected(st);
   if (grid_b) *grid_b = grid_for(st, occupancy_b(st, nz, 2), st->vlen, 2);
   if (threads) *threads = NKA_THREADS;
@@ -559,6 +558,7 @@ extern "C" int nka_comm_init(NKA st, int nranks, int rank, const void* id128)
   const int rc = g_nccl.CommInitRank(&comm, nranks, id, rank);
   if (rc != 0) return rc;
   st->comm = comm; st->own_comm = true; st->nranks = nranks; st->rank = rank;
+  set_lazy(st, false);     // a conditional second all-reduce is not worth it: every rank streams all columns
   return 0;
 }
 
@@ -567,4 +567,6 @@ extern "C" void nka_comm_adopt(NKA st, void* nccl_comm, int nranks, int rank)
   NKA_REQUIRE(st != NULL, "nka_comm_adopt: null handle");
   NKA_REQUIRE(nccl_load(), "nka_comm_adopt: libnccl.so.2 not found");
   st->comm = nccl_comm; st->own_comm = false; st->nranks = nranks; st->rank = rank;
+  DeviceGuard guard(st->device);
+  set_lazy(st, false);
 }

@@ -1,18 +1,23 @@
 // nka_kernels.cuh -- the sm_100a kernels of accel_update.
 //
-//   nka_pass_a       one read-only sweep: every difference d_j of the subspace is
-//                    formed in registers from the raw cached inputs and reduced
-//                    against d_0 and f (2*ncol dot products), deterministic
-//                    two-stage reduction, last CTA folds the per-CTA partials.
-//                    Replaces src-C/nonlinear_krylov_accelerator.c:299-301,
-//                    :323-324 and the dp() calls of :406.
-//   nka_state_kernel one thread: nka_state_step() (nka_state.h).  :333-417
-//   nka_materialise  rare: W[dst] -= W[sub] after a vtol drop / relax broke a chain.
-//   nka_pass_b       one sweep: correction, new cached columns.  :397-398, :419-430
+//   nka_pass_a        one read-only sweep: every difference d_j of the subspace is
+//                     formed in registers from the raw cached inputs and reduced
+//                     against d_0 and f (2*ncol dot products); deterministic
+//                     two-stage reduction; the last CTA folds the per-CTA partials
+//                     and (single GPU) runs the scalar state step in place.
+//                     Replaces src-C/nonlinear_krylov_accelerator.c:299-301,
+//                     :323-324, the dp() calls of :406, and :333-417.
+//   nka_state_kernel  the scalar state step alone (multi-GPU: after the all-reduce).
+//   nka_fixup_kernel  rare: the two dot products of the lazily skipped oldest
+//                     column, then the state step again.  Exits at once otherwise.
+//   nka_materialise   rare, relax() only: W[dst] -= W[sub] after a chain break.
+//   nka_pass_b        one sweep: rebuild the pending correction, form the new
+//                     pair's Z column, the accelerated correction, cache the raw
+//                     f.  Replaces :316-320, :397-398, :419-430.
 //
-// All kernels are HBM-bandwidth bound (0.2-0.4 flop/byte, fp64); tensor cores
-// do not apply.  Loads are 16-byte (double2) and coalesced; the grid is a
-// multiple of the SM count.
+// All streaming kernels are HBM-bandwidth bound (0.2-0.4 flop/byte, fp64);
+// tensor cores do not apply.  Loads/stores are 16-byte (double2), coalesced,
+// with streaming cache hints; grids are multiples of the SM count.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -20,36 +25,54 @@
 
 #include "nka_state.h"
 
-// Tunables (profiles/ records the sweep that picked the defaults).
+// Tunables (profiles/ records the sweeps that picked the defaults).
 #ifndef NKA_THREADS
 #define NKA_THREADS 256
 #endif
 #ifndef NKA_MINB_A
-#define NKA_MINB_A 1      // __launch_bounds__ min CTAs/SM for pass A (2 caps it at 128 registers)
+#define NKA_MINB_A 1      // __launch_bounds__ min CTAs/SM for pass A
 #endif
 #ifndef NKA_MINB_B
 #define NKA_MINB_B 1
+#endif
+#ifndef NKA_STORE_STREAM
+#define NKA_STORE_STREAM 1   // 1: st.global.cs for the cached columns, 0: default write-back policy
+#endif
+#ifndef NKA_LOAD_STREAM
+#define NKA_LOAD_STREAM 1    // 1: ld.global.cs (evict-first) for subspace columns, 0: ld.global.nc
 #endif
 #define NKA_STATE_THREADS 128
 
 // ---------------------------------------------------------------------------
 // 16-byte / 8-byte element access with streaming cache hints.  V = 2 uses
 // double2 (LDG.E.128 / STG.E.128), V = 1 is the fallback for a caller's f that
-// is not 16-byte aligned.
+// is not 16-byte aligned, and handles the odd tail element.
 // ---------------------------------------------------------------------------
 template <int V> struct Vec;
 template <> struct Vec<2> {
   double x, y;
   static __device__ __forceinline__ Vec ld(const double* p, size_t i) {
+#if NKA_LOAD_STREAM
     const double2 t = __ldcs(reinterpret_cast<const double2*>(p) + i);
+#else
+    const double2 t = __ldg(reinterpret_cast<const double2*>(p) + i);
+#endif
     return {t.x, t.y};
   }
   static __device__ __forceinline__ Vec ld_keep(const double* p, size_t i) {
     const double2 t = __ldg(reinterpret_cast<const double2*>(p) + i);
     return {t.x, t.y};
   }
+  static __device__ __forceinline__ Vec ld_plain(const double* p, size_t i) {
+    const double2 t = reinterpret_cast<const double2*>(p)[i];
+    return {t.x, t.y};
+  }
   __device__ __forceinline__ void st_stream(double* p, size_t i) const {
+#if NKA_STORE_STREAM
     __stcs(reinterpret_cast<double2*>(p) + i, make_double2(x, y));
+#else
+    reinterpret_cast<double2*>(p)[i] = make_double2(x, y);
+#endif
   }
   __device__ __forceinline__ void st(double* p, size_t i) const {
     reinterpret_cast<double2*>(p)[i] = make_double2(x, y);
@@ -57,7 +80,6 @@ template <> struct Vec<2> {
   static __device__ __forceinline__ Vec zero() { return {0.0, 0.0}; }
   __device__ __forceinline__ Vec operator-(const Vec& o) const { return {x - o.x, y - o.y}; }
   __device__ __forceinline__ Vec operator+(const Vec& o) const { return {x + o.x, y + o.y}; }
-  __device__ __forceinline__ Vec scaled(double a) const { return {a * x, a * y}; }
   __device__ __forceinline__ void fma_into(double a, Vec& acc) const { acc.x = fma(a, x, acc.x); acc.y = fma(a, y, acc.y); }
   __device__ __forceinline__ void dot_into(const Vec& o, double& acc) const { acc = fma(x, o.x, acc); acc = fma(y, o.y, acc); }
 };
@@ -65,12 +87,12 @@ template <> struct Vec<1> {
   double x;
   static __device__ __forceinline__ Vec ld(const double* p, size_t i) { return {__ldcs(p + i)}; }
   static __device__ __forceinline__ Vec ld_keep(const double* p, size_t i) { return {__ldg(p + i)}; }
+  static __device__ __forceinline__ Vec ld_plain(const double* p, size_t i) { return {p[i]}; }
   __device__ __forceinline__ void st_stream(double* p, size_t i) const { __stcs(p + i, x); }
   __device__ __forceinline__ void st(double* p, size_t i) const { p[i] = x; }
   static __device__ __forceinline__ Vec zero() { return {0.0}; }
   __device__ __forceinline__ Vec operator-(const Vec& o) const { return {x - o.x}; }
   __device__ __forceinline__ Vec operator+(const Vec& o) const { return {x + o.x}; }
-  __device__ __forceinline__ Vec scaled(double a) const { return {a * x}; }
   __device__ __forceinline__ void fma_into(double a, Vec& acc) const { acc.x = fma(a, x, acc.x); }
   __device__ __forceinline__ void dot_into(const Vec& o, double& acc) const { acc = fma(x, o.x, acc); }
 };
@@ -83,9 +105,103 @@ __device__ __forceinline__ double nka_warp_sum(double v)
 }
 
 // ---------------------------------------------------------------------------
+// Deterministic grid reduction of K per-thread accumulators: shuffle tree inside
+// each warp, fixed-order sum across warps, one partial row per CTA, and the last
+// CTA to take a ticket folds the rows in a fixed order (run-to-run bit-stable for
+// a given grid).  Returns true in every thread of that last CTA, after out(j, v)
+// has been called for each j.  Atomic-free except for the ticket.
+// ---------------------------------------------------------------------------
+template <int K, typename Out>
+__device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* __restrict__ partials,
+                                                unsigned* __restrict__ ticket, Out out)
+{
+  __shared__ double red[NKA_THREADS / 32][K];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const double v = nka_warp_sum(acc[j]);
+    if (lane == 0) red[warp][j] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < NKA_THREADS / 32; ++w) v += red[w][threadIdx.x];
+    partials[(size_t)blockIdx.x * K + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!is_last) return false;
+  __threadfence();
+  for (int j = warp; j < K; j += NKA_THREADS / 32) {
+    double v = 0.0;
+    for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(&partials[(size_t)b * K + j]);
+    v = nka_warp_sum(v);
+    if (lane == 0) out(j, v);
+  }
+  if (threadIdx.x == 0) *ticket = 0u;
+  __syncthreads();
+  return true;
+}
+
+// ---------------------------------------------------------------------------
+// State staging.  The ~11 KB state is worked on in shared memory: the scalar
+// algorithm is a chain of dependent loads, and from global memory every one of
+// them paid an L2 round trip (43 us at mvec = 10 on B200; profiles/r1a_*).
+// ---------------------------------------------------------------------------
+struct NkaStateStage {
+  NkaDevState st;
+  double dots[2 * NKA_MAXSLOT];
+};
+
+__device__ __forceinline__ void nka_stage_in(NkaStateStage& sm, const NkaDevState* S, const double* dots)
+{
+  static_assert(sizeof(NkaDevState) % 4 == 0, "state is copied in 4-byte words");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(S);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.st);
+  for (unsigned i = threadIdx.x; i < sizeof(NkaDevState) / 4; i += blockDim.x) dst[i] = __ldcg(src + i);
+  if (dots)
+    for (unsigned i = threadIdx.x; i < 2 * NKA_MAXSLOT; i += blockDim.x) sm.dots[i] = __ldcg(dots + i);
+  __syncthreads();
+}
+
+__device__ __forceinline__ void nka_stage_out(const NkaStateStage& sm, NkaDevState* S)
+{
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.st);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(S);
+  for (unsigned i = threadIdx.x; i < sizeof(NkaDevState) / 4; i += blockDim.x) dst[i] = src[i];
+}
+
+// One copy of the scalar step per translation unit (it is inlined nowhere: pass A is
+// instantiated 66 times and would otherwise carry 66 copies of it).
+static __device__ __noinline__ int nka_state_step_dev(NkaDevState* st, const double* dots, int have_last)
+{
+  return nka_state_step(*st, dots, NKA_MAXSLOT, have_last);
+}
+
+// Runs the step on the staged copy (dots already in sm.dots) and commits it,
+// unless it needs the lazily skipped column: then only the flag is published.
+__device__ __forceinline__ void nka_run_state_step(NkaStateStage& sm, NkaDevState* S, int have_last)
+{
+  __shared__ int need_more;
+  if (threadIdx.x == 0) need_more = nka_state_step_dev(&sm.st, sm.dots, have_last);
+  __syncthreads();
+  if (need_more) {
+    if (threadIdx.x == 0) S->need_fixup = 1;
+  } else {
+    nka_stage_out(sm, S);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Pass A.
-//   acc[j]      += d_0 . d_j      acc[NC + j] += f . d_j       (j < ncol <= NC)
-// One body, instantiated for V = 2 on the bulk and V = 1 on the odd tail.
+//   acc[j]      += d_0 . d_j      acc[NC + j] += f . d_j       (j < ncol_eff <= NC)
 // FULL = the plan streams exactly NC chained columns: no predicates at all.
 // ---------------------------------------------------------------------------
 template <int NC, int V, bool FULL>
@@ -117,10 +233,10 @@ __device__ __forceinline__ void nka_pass_a_elem(const double* __restrict__ f, co
 template <int NC, int V>
 __global__ void __launch_bounds__(NKA_THREADS, NKA_MINB_A)
 nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld, size_t n,
-           const NkaDevState* __restrict__ S, double* __restrict__ partials, unsigned* __restrict__ ticket,
-           double* __restrict__ dots)
+           NkaDevState* __restrict__ S, double* __restrict__ partials, unsigned* __restrict__ ticket,
+           double* __restrict__ dots, int fuse_state)
 {
-  const int ncol = S->planA.ncol;
+  const int ncol = S->planA.ncol - S->planA.skip_last;      // columns actually streamed
   const unsigned submask = S->planA.submask;
   const double* wcol[NC];
 #pragma unroll
@@ -133,7 +249,8 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
   const size_t nv = n / V;
   const size_t stride = (size_t)gridDim.x * NKA_THREADS;
   const size_t start = (size_t)blockIdx.x * NKA_THREADS + threadIdx.x;
-  const bool full = (ncol == NC) && (submask == (NC >= 32 ? 0xffffffffu : ((1u << NC) - 1u)));
+  const unsigned allbits = NC >= 32 ? 0xffffffffu : ((1u << NC) - 1u);
+  const bool full = (ncol == NC) && ((submask & allbits) == allbits);
   if (full) {
     for (size_t i = start; i < nv; i += stride) nka_pass_a_elem<NC, V, true>(f, wcol, i, ncol, submask, acc);
   } else {
@@ -141,136 +258,36 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
   }
   if (V == 2 && (n & 1) && start == 0) nka_pass_a_elem<NC, 1, false>(f, wcol, n - 1, ncol, submask, acc);
 
-  // block reduction: shuffle tree inside each warp, fixed-order sum across warps
-  __shared__ double red[NKA_THREADS / 32][2 * NC];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int j = 0; j < 2 * NC; ++j) {
-    const double v = nka_warp_sum(acc[j]);
-    if (lane == 0) red[warp][j] = v;
-  }
-  __syncthreads();
-  if (threadIdx.x < 2 * NC) {
-    double v = 0.0;
-#pragma unroll
-    for (int w = 0; w < NKA_THREADS / 32; ++w) v += red[w][threadIdx.x];
-    partials[(size_t)blockIdx.x * (2 * NC) + threadIdx.x] = v;
-  }
-
-  // last CTA to finish folds the per-CTA partials in a fixed order (run-to-run bit-stable)
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(ticket, 1u);
-    is_last = (t == gridDim.x - 1);
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  for (int j = warp; j < 2 * NC; j += NKA_THREADS / 32) {
-    double v = 0.0;
-    for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(&partials[(size_t)b * (2 * NC) + j]);
-    v = nka_warp_sum(v);
-    if (lane == 0) dots[(j < NC) ? j : (NKA_MAXSLOT + (j - NC))] = v;
-  }
-  if (threadIdx.x == 0) *ticket = 0u;
-}
-
-// ---------------------------------------------------------------------------
-// State kernels.  The ~10 KB state is staged through shared memory: the scalar
-// algorithm is a chain of dependent loads, and from global memory every one of
-// them paid an L2 round trip (43 us at mvec = 10 on B200; see profiles/).
-// ---------------------------------------------------------------------------
-struct NkaStateStage {
-  NkaDevState st;
-  double dots[2 * NKA_MAXSLOT];
-};
-
-__device__ __forceinline__ void nka_stage_in(NkaStateStage& sm, const NkaDevState* S, const double* dots)
-{
-  static_assert(sizeof(NkaDevState) % 4 == 0, "state is copied in 4-byte words");
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(S);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.st);
-  for (unsigned i = threadIdx.x; i < sizeof(NkaDevState) / 4; i += blockDim.x) dst[i] = __ldcg(src + i);
-  if (dots)
-    for (unsigned i = threadIdx.x; i < 2 * NKA_MAXSLOT; i += blockDim.x) sm.dots[i] = __ldcg(dots + i);
-  __syncthreads();
-}
-
-__device__ __forceinline__ void nka_stage_out(const NkaStateStage& sm, NkaDevState* S)
-{
-  __syncthreads();
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(&sm.st);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(S);
-  for (unsigned i = threadIdx.x; i < sizeof(NkaDevState) / 4; i += blockDim.x) dst[i] = src[i];
-}
-
-__global__ void __launch_bounds__(NKA_STATE_THREADS) nka_state_kernel(NkaDevState* S, const double* dots)
-{
-  __shared__ NkaStateStage sm;
-  nka_stage_in(sm, S, dots);
-  if (threadIdx.x == 0) nka_state_step(sm.st, sm.dots, NKA_MAXSLOT);
-  nka_stage_out(sm, S);
-}
-
-__global__ void __launch_bounds__(NKA_STATE_THREADS) nka_relax_kernel(NkaDevState* S)
-{
-  __shared__ NkaStateStage sm;
-  nka_stage_in(sm, S, nullptr);
-  if (threadIdx.x == 0) nka_state_relax(sm.st);
-  nka_stage_out(sm, S);
-}
-
-__global__ void __launch_bounds__(NKA_STATE_THREADS) nka_restart_kernel(NkaDevState* S)
-{
-  __shared__ NkaStateStage sm;
-  nka_stage_in(sm, S, nullptr);
-  if (threadIdx.x == 0) nka_state_restart(sm.st);
-  nka_stage_out(sm, S);
-}
-
-__global__ void nka_init_kernel(NkaDevState* S, int mvec, double vtol)
-{
-  if (threadIdx.x == 0 && blockIdx.x == 0) nka_state_init(*S, mvec, vtol);
-}
-
-__global__ void nka_set_vtol_kernel(NkaDevState* S, double vtol)
-{
-  if (threadIdx.x == 0 && blockIdx.x == 0) S->vtol = vtol;
-}
-
-// ---------------------------------------------------------------------------
-// Materialise: W[dst] -= W[sub] for each plan entry, oldest first, per element.
-// Exits at once when the plan is empty (the common case).
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(NKA_THREADS)
-nka_materialise(double* W, size_t ld, size_t n, const NkaDevState* __restrict__ S)
-{
-  const int m = S->planM.n;
-  if (m == 0) return;
-  const size_t stride = (size_t)gridDim.x * NKA_THREADS;
-  for (size_t i = (size_t)blockIdx.x * NKA_THREADS + threadIdx.x; i < n; i += stride) {
-    for (int e = 0; e < m; ++e) {
-      double* dst = W + (size_t)S->planM.dst[e] * ld;
-      const double* sub = W + (size_t)S->planM.sub[e] * ld;
-      dst[i] = dst[i] - sub[i];
-    }
+  __shared__ NkaStateStage sm;     // used by the last CTA only
+  const bool last = nka_grid_reduce<2 * NC>(acc, partials, ticket, [&](int j, double v) {
+    const int at = (j < NC) ? j : (NKA_MAXSLOT + (j - NC));
+    dots[at] = v;
+    sm.dots[at] = v;
+  });
+  if (last && fuse_state) {
+    // single GPU: the scalar step runs right here, no extra launch
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(S);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.st);
+    for (unsigned i = threadIdx.x; i < sizeof(NkaDevState) / 4; i += blockDim.x) dst[i] = __ldcg(src + i);
+    __syncthreads();
+    nka_run_state_step(sm, S, /*have_last=*/0);
   }
 }
 
 // ---------------------------------------------------------------------------
-// Pass B.  NZ is the host's expectation of how many older Z columns the plan
-// keeps (exact unless a vtol drop or the s == 0 guard fired); the FULL body is
-// predicate-free.  Any other plan goes through the general body, which also
-// handles nz > NZ with a run-time loop over the extra columns.
+// Pass B.  NZ is the host's expectation of how many pairs were on the list at
+// entry (exact unless a vtol drop fired earlier); the FULL body is predicate-free.
+// Any other plan goes through the general body, which handles nz != NZ, a missing
+// pair, and the chain-break conversions W[dst] -= W[sub] (same thread, same
+// element, before W[newslot] is overwritten, so no cross-thread hazard exists).
 // ---------------------------------------------------------------------------
 template <int NZ, int V, bool FULL>
-__device__ __forceinline__ void nka_pass_b_elem(double* __restrict__ f, double* __restrict__ wnew, double* __restrict__ znew,
-                                                double* __restrict__ zp, const double* const (&zcol)[NZ > 0 ? NZ : 1],
-                                                const double (&coef)[NZ > 0 ? NZ : 1], double coef_p,
+__device__ __forceinline__ void nka_pass_b_elem(double* __restrict__ f, double* __restrict__ wnew, double* __restrict__ zp,
+                                                const double* const (&zcol)[NZ > 0 ? NZ : 1],
+                                                const double (&coefN)[NZ > 0 ? NZ : 1],
+                                                const double (&coefY)[NZ > 0 ? NZ : 1], double coef_p,
                                                 int has_pair, int nz, int write_f, size_t i,
-                                                const double* __restrict__ Z, size_t ld, const NkaPlanB* __restrict__ B)
+                                                double* W, const double* Z, size_t ld, const NkaDevState* S)
 {
   using T = Vec<V>;
   const T x0 = T::ld(f, i);
@@ -280,56 +297,65 @@ __device__ __forceinline__ void nka_pass_b_elem(double* __restrict__ f, double* 
     if (FULL || k < nz) zs[k] = T::ld(zcol[k], i);
     else zs[k] = T::zero();
   }
+  if (!FULL) {
+    const int m = S->planM.n;
+    for (int e = 0; e < m; ++e) {
+      double* dst = W + (size_t)S->planM.dst[e] * ld;
+      const double* sub = W + (size_t)S->planM.sub[e] * ld;
+      (T::ld_plain(dst, i) - T::ld_plain(sub, i)).st(dst, i);
+    }
+    // W[newslot] may be one of the `sub` columns: keep its overwrite below after these reads
+    if (m > 0) asm volatile("" ::: "memory");
+  }
   T y = T::zero();
   if (FULL || has_pair) {
-    const T zpv = T::ld(zp, i) + x0;        // Z'_p = Y_p + f
+    T yprev = T::zero();                     // the previous call's correction, same fma order as then
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) zs[k].fma_into(coefY[k], yprev);
+    if (!FULL)
+      for (int k = NZ; k < nz; ++k) T::ld(Z + (size_t)S->planB.zcol[k] * ld, i).fma_into(S->planB.coefY[k], yprev);
+    const T zpv = yprev + x0;                // Z'_p = Y_p + f
     zpv.st_stream(zp, i);
     zpv.fma_into(coef_p, y);
   }
 #pragma unroll
-  for (int k = 0; k < NZ; ++k) zs[k].fma_into(coef[k], y);   // coef is 0 beyond nz
-  if (!FULL) {
-    for (int k = NZ; k < nz; ++k) {
-      const T z = T::ld(Z + (size_t)B->zcol[k] * ld, i);
-      z.fma_into(B->coef[k], y);
-    }
-  }
-  y.st_stream(znew, i);
+  for (int k = 0; k < NZ; ++k) zs[k].fma_into(coefN[k], y);
+  if (!FULL)
+    for (int k = NZ; k < nz; ++k) T::ld(Z + (size_t)S->planB.zcol[k] * ld, i).fma_into(S->planB.coefN[k], y);
   x0.st_stream(wnew, i);
   if (FULL || write_f) (x0 + y).st(f, i);
 }
 
 template <int NZ, int V>
 __global__ void __launch_bounds__(NKA_THREADS, NKA_MINB_B)
-nka_pass_b(double* __restrict__ f, double* __restrict__ W, double* __restrict__ Z, size_t ld, size_t n,
-           const NkaDevState* __restrict__ S)
+nka_pass_b(double* __restrict__ f, double* W, double* Z, size_t ld, size_t n, const NkaDevState* __restrict__ S)
 {
   constexpr int NZA = NZ > 0 ? NZ : 1;
   const NkaPlanB* B = &S->planB;
   const int nz = B->nz, has_pair = B->has_pair, write_f = B->write_f;
   double* wnew = W + (size_t)B->newslot * ld;
-  double* znew = Z + (size_t)B->newslot * ld;
   double* zp = Z + (size_t)B->pslot * ld;
   const double coef_p = B->coef_p;
   const double* zcol[NZA];
-  double coef[NZA];
+  double coefN[NZA], coefY[NZA];
 #pragma unroll
   for (int k = 0; k < NZA; ++k) {
     const bool on = (k < nz) && (k < NZ);
     zcol[k] = Z + (size_t)(on ? B->zcol[k] : B->newslot) * ld;
-    coef[k] = on ? B->coef[k] : 0.0;
+    coefN[k] = on ? B->coefN[k] : 0.0;
+    coefY[k] = on ? B->coefY[k] : 0.0;
   }
   const size_t nv = n / V;
   const size_t stride = (size_t)gridDim.x * NKA_THREADS;
   const size_t start = (size_t)blockIdx.x * NKA_THREADS + threadIdx.x;
-  const bool full = (nz == NZ) && has_pair && write_f;
+  const bool full = (nz == NZ) && has_pair && write_f && (S->planM.n == 0);
   if (full) {
     for (size_t i = start; i < nv; i += stride)
-      nka_pass_b_elem<NZ, V, true>(f, wnew, znew, zp, zcol, coef, coef_p, has_pair, nz, write_f, i, Z, ld, B);
+      nka_pass_b_elem<NZ, V, true>(f, wnew, zp, zcol, coefN, coefY, coef_p, has_pair, nz, write_f, i, W, Z, ld, S);
   } else {
     for (size_t i = start; i < nv; i += stride)
-      nka_pass_b_elem<NZ, V, false>(f, wnew, znew, zp, zcol, coef, coef_p, has_pair, nz, write_f, i, Z, ld, B);
+      nka_pass_b_elem<NZ, V, false>(f, wnew, zp, zcol, coefN, coefY, coef_p, has_pair, nz, write_f, i, W, Z, ld, S);
   }
   if (V == 2 && (n & 1) && start == 0)
-    nka_pass_b_elem<NZ, 1, false>(f, wnew, znew, zp, zcol, coef, coef_p, has_pair, nz, write_f, n - 1, Z, ld, B);
+    nka_pass_b_elem<NZ, 1, false>(f, wnew, zp, zcol, coefN, coefY, coef_p, has_pair, nz, write_f, n - 1, W, Z, ld, S);
 }

@@ -15,9 +15,15 @@
 //   is  w_k = (W[k] - W[prev[k]]) / s[k].  A slot whose newer neighbour leaves
 //   the list is "materialised": W[k] <- W[k] - W[prev k], chained[k] = 0, and
 //   from then on w_k = W[k] / s[k].
-//   Z[k] holds, for the pending slot, Y = f_out - f_in of the call that created
-//   it; for a finished pair, Z'_k = Y_k + f_next, so that
+//   Z[k] holds, for a finished pair, Z'_k = Y_k + f_next, where Y_k = f_out - f_in
+//   is the correction applied by the call that created slot k, so that
 //   v_k - w_k = Z[k] / s[k]   (reference v, w: src-C/...c:316-320, :423).
+//   Y of the pending slot is NOT stored: it is a linear combination of columns
+//   pass B reads anyway, so the next pass B recomputes it from the saved
+//   coefficients coefY[] (one column write less per update).
+//   Lazy last column: when the list is full the oldest pair is evicted unless a
+//   vtol drop makes room; pass A then skips its column (skip_last) and the rare
+//   case that needs it after all runs a two-dot fix-up sweep (need_fixup).
 #pragma once
 
 #if defined(__CUDACC__)
@@ -42,7 +48,8 @@
 // each difference is formed:  d_j = W[col[j]] - (bit j of submask ? prev : 0),
 // prev = f for j == 0, W[col[j-1]] otherwise.
 struct NkaPlanA {
-  int ncol;
+  int ncol;          // list length on entry
+  int skip_last;     // 1: pass A leaves out col[ncol-1] (it will be evicted unless a drop occurs)
   unsigned submask;
   int col[NKA_MAXSLOT];
 };
@@ -54,9 +61,11 @@ struct NkaPlanM {
   int sub[NKA_MAXSLOT];
 };
 
-// What pass B does:  Z[pslot] <- Z[pslot] + f (if has_pair);
-//   y = coef_p * Z[pslot] + sum_k coef[k] * Z[zcol[k]];
-//   Z[newslot] <- y;  W[newslot] <- f;  f <- f + y (if write_f).
+// What pass B does, with z_k = Z[zcol[k]] (the pairs on the list at entry, newest first):
+//   if has_pair:  Y = sum_k coefY[k] z_k  (the previous call's correction, recomputed);
+//                 zp = Y + f;  Z[pslot] <- zp
+//   y = coef_p * zp + sum_k coefN[k] z_k      (coefN = 0 for pairs dropped this call)
+//   W[newslot] <- f;  f <- f + y (if write_f).
 struct NkaPlanB {
   int newslot;
   int has_pair;
@@ -65,7 +74,8 @@ struct NkaPlanB {
   int nz;
   int zcol[NKA_MAXSLOT];
   double coef_p;
-  double coef[NKA_MAXSLOT];
+  double coefN[NKA_MAXSLOT];
+  double coefY[NKA_MAXSLOT];
 };
 
 struct NkaDevState {
@@ -79,7 +89,10 @@ struct NkaDevState {
   double c[NKA_MAXSLOT];
   // --- raw-chain bookkeeping
   double s[NKA_MAXSLOT];                 // norm of the raw difference of pair k
+  double coefY[NKA_MAXSLOT];             // coefficient of Z[k] in the last correction y (0 if absent)
   int chained[NKA_MAXSLOT];
+  int lazy_last;                         // feature switch: allow pass A to skip the doomed oldest column
+  int need_fixup;                        // phase 1 found it needs the skipped column after all
   // --- plans
   NkaPlanA planA;
   NkaPlanM planM;
@@ -105,6 +118,7 @@ NKA_HD void nka_build_plan_a(NkaDevState& S)
   }
   A.ncol = j;
   A.submask = mask;
+  A.skip_last = (S.lazy_last && S.pending && j == S.mvec + 1) ? 1 : 0;
 }
 
 NKA_HD void nka_state_restart(NkaDevState& S)
@@ -117,8 +131,9 @@ NKA_HD void nka_state_restart(NkaDevState& S)
   S.free_ = 0;
   for (int k = 0; k < S.mvec; ++k) S.next[k] = k + 1;
   S.next[S.mvec] = NKA_NIL;
-  for (int k = 0; k <= S.mvec; ++k) { S.prev[k] = NKA_NIL; S.chained[k] = 0; }
+  for (int k = 0; k <= S.mvec; ++k) { S.prev[k] = NKA_NIL; S.chained[k] = 0; S.coefY[k] = 0.0; }
   S.planM.n = 0;
+  S.need_fixup = 0;
   nka_build_plan_a(S);
 }
 
@@ -132,7 +147,8 @@ NKA_HD void nka_state_init(NkaDevState& S, int mvec, double vtol)
   S.min_margin = 0.0;
   S.s_last = 0.0;
   for (int i = 0; i < NKA_MAXSLOT * NKA_MAXSLOT; ++i) S.h[i] = 0.0;
-  for (int i = 0; i < NKA_MAXSLOT; ++i) { S.c[i] = 0.0; S.s[i] = 1.0; }
+  for (int i = 0; i < NKA_MAXSLOT; ++i) { S.c[i] = 0.0; S.s[i] = 1.0; S.coefY[i] = 0.0; }
+  S.lazy_last = 1;
   S.planB.newslot = 0; S.planB.has_pair = 0; S.planB.pslot = 0; S.planB.write_f = 0; S.planB.nz = 0;
   S.planB.coef_p = 0.0;
   nka_state_restart(S);
@@ -193,16 +209,23 @@ NKA_HD void nka_state_relax(NkaDevState& S)
 // The scalar part of one accel_update.  `dots` holds what pass A reduced, laid
 // out as dd[j] = d_0 . d_j  (j < ncol)  followed by  fd[j] = f . d_j  at
 // dots[stride + j]; ignored when the list was empty on entry.
-NKA_HD void nka_state_step(NkaDevState& S, const double* dots, int stride)
+//
+// have_last = 0 means pass A skipped the oldest column (planA.skip_last): if the
+// factorisation turns out to need it, nothing is committed and the function
+// returns 1 with need_fixup set; the caller then computes the two missing dot
+// products and calls again with have_last = 1.  Returns 0 when the step is done.
+NKA_HD int nka_state_step(NkaDevState& S, const double* dots, int stride, int have_last)
 {
   int ord[NKA_MAXSLOT];
   bool removed[NKA_MAXSLOT];
   double rhs[NKA_MAXSLOT];
   const int L = S.planA.ncol;
+  const int missing = (S.planA.skip_last && !have_last) ? L - 1 : -1;   // position without dots
   for (int j = 0; j < L; ++j) ord[j] = S.planA.col[j];
   for (int k = 0; k < NKA_MAXSLOT; ++k) { removed[k] = false; rhs[k] = 0.0; }
   const double* dd = dots;
   const double* fd = dots + stride;
+  const int pending_at_entry = S.pending;
 
   S.ndrop_last = 0;
   S.evicted_last = 0;
@@ -210,6 +233,7 @@ NKA_HD void nka_state_step(NkaDevState& S, const double* dots, int stride)
   S.min_margin = 1.0e300;
   S.s_last = 0.0;
   S.planM.n = 0;
+  S.need_fixup = 0;
   int jr = L;            // first list position whose slot left the list this call
   int has_pair = 0;
   double s = 0.0;
@@ -219,6 +243,7 @@ NKA_HD void nka_state_step(NkaDevState& S, const double* dots, int stride)
     s = NKA_SQRT(dd[0]);
     S.s_last = s;
     if (s == 0.0) {
+      if (missing >= 0) { S.need_fixup = 1; return 1; }   // every old pair stays: its f.d is needed
       removed[nka_list_relax(S)] = true;
       S.relaxed_last = 1;
       jr = 0;
@@ -234,7 +259,7 @@ NKA_HD void nka_state_step(NkaDevState& S, const double* dots, int stride)
     // <w_1, w_k> = (d_0 . d_k) / (s s_k); the reference normalises first (:317-324)
     for (int j = 1; j < L; ++j) {
       const int k = ord[j];
-      NKA_H(S, p, k) = (dd[j] / s) / S.s[k];
+      if (j != missing) NKA_H(S, p, k) = (dd[j] / s) / S.s[k];
     }
     int nvec = 1;
     NKA_H(S, p, p) = 1.0;
@@ -252,6 +277,7 @@ NKA_HD void nka_state_step(NkaDevState& S, const double* dots, int stride)
         S.evicted_last = 1;
         break;
       }
+      if (pos == missing) { S.need_fixup = 1; return 1; }   // a drop made room: the skipped column matters
       double hkk = 1.0;                            // :350-360
       for (int j = p; j != k; j = S.next[j]) {
         double hkj = NKA_H(S, j, k);
@@ -285,7 +311,7 @@ NKA_HD void nka_state_step(NkaDevState& S, const double* dots, int stride)
   if (jr < L) nka_plan_materialise(S, ord, L, jr, removed);
 
   // Step C: storage for the new vectors.  src-C/...c:391-394
-  if (S.free_ == NKA_NIL) { S.error = 2; return; }
+  if (S.free_ == NKA_NIL) { S.error = 2; return 0; }
   const int nw = S.free_;
   S.free_ = S.next[nw];
 
@@ -298,7 +324,8 @@ NKA_HD void nka_state_step(NkaDevState& S, const double* dots, int stride)
   B.nz = 0;
   B.write_f = 0;
   if (S.subspace) {
-    for (int j = 0; j < L; ++j) rhs[ord[j]] = fd[j] / S.s[ord[j]];   // <f, w_k>
+    for (int j = 0; j < L; ++j)
+      if (!removed[ord[j]]) rhs[ord[j]] = fd[j] / S.s[ord[j]];        // <f, w_k>
     for (int j = S.first; j != NKA_NIL; j = S.next[j]) {
       double cj = rhs[j];
       for (int i = S.first; i != j; i = S.next[i]) cj -= NKA_H(S, j, i) * S.c[i];
@@ -309,19 +336,23 @@ NKA_HD void nka_state_step(NkaDevState& S, const double* dots, int stride)
       for (int i = S.last; i != j; i = S.prev[i]) cj -= NKA_H(S, i, j) * S.c[i];
       S.c[j] = cj / NKA_H(S, j, j);
     }
-    // correction  f += sum_k c_k (v_k - w_k) = sum_k (c_k / s_k) Z[k]   (:419-424)
-    for (int k = S.first; k != NKA_NIL; k = S.next[k]) {
-      const double coef = S.c[k] / S.s[k];
-      if (has_pair && k == S.first) {
-        B.coef_p = coef;
-      } else {
-        B.zcol[B.nz] = k;
-        B.coef[B.nz] = coef;
-        ++B.nz;
-      }
-    }
     B.write_f = 1;
   }
+  // Pass B streams the Z column of every pair that was on the list at entry: with the old
+  // coefficient it rebuilds the pending correction Y, with the new one (0 if the pair left the
+  // list) it forms the correction  f += sum_k c_k (v_k - w_k) = sum_k (c_k / s_k) Z[k]  (:419-424).
+  for (int j = pending_at_entry ? 1 : 0; j < L; ++j) {
+    const int k = ord[j];
+    B.zcol[B.nz] = k;
+    B.coefY[B.nz] = S.coefY[k];
+    B.coefN[B.nz] = (S.subspace && !removed[k]) ? S.c[k] / S.s[k] : 0.0;
+    ++B.nz;
+  }
+  if (has_pair) B.coef_p = S.c[S.first] / S.s[S.first];
+  // remember how this call's correction y was assembled; the next pass B recomputes it
+  for (int k = 0; k <= S.mvec; ++k) S.coefY[k] = 0.0;
+  for (int i = 0; i < B.nz; ++i) S.coefY[B.zcol[i]] = B.coefN[i];
+  if (has_pair) S.coefY[S.first] = B.coef_p;
 
   // Step E: push the new slot, mark pending.  src-C/...c:432-443
   S.prev[nw] = NKA_NIL;
@@ -334,6 +365,7 @@ NKA_HD void nka_state_step(NkaDevState& S, const double* dots, int stride)
   ++S.ncalls;
 
   nka_build_plan_a(S);
+  return 0;
 }
 
 // Structural invariant check, src-F08/nka_type.F90:460-524 (0-based).

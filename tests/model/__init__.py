@@ -38,6 +38,10 @@ def lib():
             getattr(L, nm).restype = C.c_int
         L.model_mat_entries.argtypes = [C.c_void_p]
         L.model_mat_entries.restype = C.c_ulonglong
+        L.model_fixups.argtypes = [C.c_void_p]
+        L.model_fixups.restype = C.c_ulonglong
+        L.model_set_lazy.argtypes = [C.c_void_p, C.c_int]
+        L.model_set_lazy.restype = None
         L.model_min_margin.argtypes = [C.c_void_p]
         L.model_min_margin.restype = C.c_double
         _lib = L
@@ -45,12 +49,16 @@ def lib():
 
 
 class ModelNKA:
-    def __init__(self, vlen, mvec, vtol=0.01):
+    def __init__(self, vlen, mvec, vtol=0.01, lazy=True):
         self._lib = lib()
         self._h = self._lib.model_init(vlen, mvec, vtol)
         if not self._h:
             raise ValueError("bad arguments")
         self.vlen = vlen
+        if not lazy:
+            self._lib.model_set_lazy(self._h, 0)
+
+    def fixups(self): return self._lib.model_fixups(self._h)
 
     def accel_update(self, f: np.ndarray):
         assert f.dtype == np.float64 and f.shape == (self.vlen,)

@@ -27,17 +27,20 @@ struct Model {
   int ub_len;
   int bound_violations;
   unsigned long long mat_entries;
+  unsigned long long fixups;
+  bool lazy;
 };
 
 static void pass_a(Model* m, const double* f)
 {
   const NkaPlanA& A = m->S.planA;
+  const int ncol = A.ncol - A.skip_last;
   for (int j = 0; j < 2 * NKA_MAXSLOT; ++j) m->dots[j] = 0.0;
   // long double accumulation: the model checks logic, not summation order
-  std::vector<long double> dd(A.ncol, 0.0L), fd(A.ncol, 0.0L);
+  std::vector<long double> dd(ncol, 0.0L), fd(ncol, 0.0L);
   for (size_t i = 0; i < m->n; ++i) {
     double prev = f[i], d0 = 0.0;
-    for (int j = 0; j < A.ncol; ++j) {
+    for (int j = 0; j < ncol; ++j) {
       const double x = m->W[(size_t)A.col[j] * m->ld + i];
       const double d = ((A.submask >> j) & 1u) ? x - prev : x;
       if (j == 0) d0 = d;
@@ -46,7 +49,25 @@ static void pass_a(Model* m, const double* f)
       prev = x;
     }
   }
-  for (int j = 0; j < A.ncol; ++j) { m->dots[j] = (double)dd[j]; m->dots[NKA_MAXSLOT + j] = (double)fd[j]; }
+  for (int j = 0; j < ncol; ++j) { m->dots[j] = (double)dd[j]; m->dots[NKA_MAXSLOT + j] = (double)fd[j]; }
+}
+
+// the two dot products of the skipped oldest column (nka_fixup_kernel)
+static void fixup(Model* m, const double* f)
+{
+  const NkaPlanA& A = m->S.planA;
+  const int jl = A.ncol - 1;
+  long double dd = 0.0L, fd = 0.0L;
+  for (size_t i = 0; i < m->n; ++i) {
+    const double d0 = m->W[(size_t)A.col[0] * m->ld + i] - f[i];
+    const double xl = m->W[(size_t)A.col[jl] * m->ld + i];
+    const double dl = ((A.submask >> jl) & 1u) ? xl - m->W[(size_t)A.col[jl - 1] * m->ld + i] : xl;
+    dd += (long double)d0 * dl;
+    fd += (long double)f[i] * dl;
+  }
+  m->dots[jl] = (double)dd;
+  m->dots[NKA_MAXSLOT + jl] = (double)fd;
+  m->fixups++;
 }
 
 static void materialise(Model* m)
@@ -61,16 +82,21 @@ static void materialise(Model* m)
 static void pass_b(Model* m, double* f)
 {
   const NkaPlanB& B = m->S.planB;
+  const NkaPlanM& P = m->S.planM;
+  m->mat_entries += P.n;
   for (size_t i = 0; i < m->n; ++i) {
     const double x0 = f[i];
+    for (int e = 0; e < P.n; ++e)
+      m->W[(size_t)P.dst[e] * m->ld + i] -= m->W[(size_t)P.sub[e] * m->ld + i];
     double y = 0.0;
     if (B.has_pair) {
-      double& zp = m->Z[(size_t)B.pslot * m->ld + i];
-      zp = zp + x0;
+      double yprev = 0.0;
+      for (int k = 0; k < B.nz; ++k) yprev += B.coefY[k] * m->Z[(size_t)B.zcol[k] * m->ld + i];
+      const double zp = yprev + x0;
+      m->Z[(size_t)B.pslot * m->ld + i] = zp;
       y += B.coef_p * zp;
     }
-    for (int k = 0; k < B.nz; ++k) y += B.coef[k] * m->Z[(size_t)B.zcol[k] * m->ld + i];
-    m->Z[(size_t)B.newslot * m->ld + i] = y;
+    for (int k = 0; k < B.nz; ++k) y += B.coefN[k] * m->Z[(size_t)B.zcol[k] * m->ld + i];
     m->W[(size_t)B.newslot * m->ld + i] = x0;
     if (B.write_f) f[i] = x0 + y;
   }
@@ -87,7 +113,7 @@ Model* model_init(size_t n, int mvec, double vtol)
   m->W.assign(m->ld * (mvec + 1), 0.0);
   m->Z.assign(m->ld * (mvec + 1), 0.0);
   nka_state_init(m->S, mvec, vtol);
-  m->pending = false; m->ub_len = 0; m->bound_violations = 0; m->mat_entries = 0;
+  m->pending = false; m->ub_len = 0; m->bound_violations = 0; m->mat_entries = 0; m->fixups = 0; m->lazy = true;
   return m;
 }
 
@@ -96,16 +122,32 @@ void model_delete(Model* m) { delete m; }
 void model_accel_update(Model* m, double* f)
 {
   const int L = m->ub_len;
-  if (m->S.planA.ncol > L) m->bound_violations++;
-  if (L > 0) pass_a(m, f);
-  nka_state_step(m->S, m->dots, NKA_MAXSLOT);
-  if (L >= 2) materialise(m);
-  else if (m->S.planM.n != 0) m->bound_violations++;
+  const bool may_skip = m->lazy && m->pending && L == m->mvec + 1;
+  const int NC = may_skip ? m->mvec : L;
+  if (m->S.planA.ncol - m->S.planA.skip_last > NC) m->bound_violations++;
+  if (m->S.planA.skip_last && !may_skip) m->bound_violations++;
+  if (L > 0) {
+    pass_a(m, f);
+    NkaDevState copy = m->S;                       // the device works on a staged copy
+    if (nka_state_step(copy, m->dots, NKA_MAXSLOT, 0)) {
+      if (!may_skip) m->bound_violations++;        // the host must have queued the fix-up kernel
+      m->S.need_fixup = 1;
+      fixup(m, f);
+      copy = m->S;
+      if (nka_state_step(copy, m->dots, NKA_MAXSLOT, 1)) m->bound_violations++;
+    }
+    m->S = copy;
+  } else {
+    nka_state_step(m->S, m->dots, NKA_MAXSLOT, 1);
+  }
   pass_b(m, f);
   if (m->pending) m->ub_len = L + 1 < m->mvec + 1 ? L + 1 : m->mvec + 1;
   else m->ub_len = L + 1;
   m->pending = true;
 }
+
+void model_set_lazy(Model* m, int on) { m->lazy = on != 0; m->S.lazy_last = on; nka_build_plan_a(m->S); }
+unsigned long long model_fixups(Model* m) { return m->fixups; }
 
 void model_restart(Model* m) { nka_state_restart(m->S); m->pending = false; m->ub_len = 0; }
 

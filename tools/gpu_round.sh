@@ -16,13 +16,13 @@ bench)
 ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$tag.csv \
      python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_list_$tag.log 2>&1
-  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:nka_pass -s 34 -c 4 -f -o gpurun_out/prof_$tag \
+  timeout 1200 ncu --set full --clock-control none --import-source on -k regex:nka_pass -s 30 -c 4 -f -o gpurun_out/prof_$tag \
      python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_$tag.log 2>&1
   ls -la gpurun_out/prof_$tag.ncu-rep ;;
 tune)
   : > gpurun_out/tune_$tag.jsonl
-  for lib in default t256_b2 t256_b3 t512_b1 t128_b4 t128_b3; do
-    for g in 0 1 2 3 4 6 8; do
+  for lib in ${TUNE_LIBS:-default t256_b2 t512_b1 t256_b1_st0 t512_b1_st0 t512_b1_ld0 t1024_b1}; do
+    for g in ${TUNE_GRIDS:-0 2 4 8}; do
       if [ $lib = default ]; then unset NKA_B200_LIB; else export NKA_B200_LIB=$PWD/nka_b200/lib/variants/libnka_b200_$lib.so; fi
       if [ $g = 0 ]; then unset NKA_GRID_PER_SM_A NKA_GRID_PER_SM_B; else export NKA_GRID_PER_SM_A=$g NKA_GRID_PER_SM_B=$g; fi
       TUNE_TAG="$lib/g$g" timeout 120 python tools/tune.py >> gpurun_out/tune_$tag.jsonl 2>> gpurun_out/tune_$tag.err

@@ -17,6 +17,7 @@ def main():
     n = int(os.environ.get("TUNE_N", str(1 << 28)))
     m = int(os.environ.get("TUNE_M", "10"))
     steps = int(os.environ.get("TUNE_STEPS", "30"))
+    lazy = os.environ.get("NKA_LAZY_LAST", "1") != "0"
     acc = NKA(n, m, 0.01)
     gen = torch.Generator(device="cuda").manual_seed(5)
     pool = [torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) - 0.5 for _ in range(m + 3)]
@@ -40,7 +41,8 @@ def main():
         "tag": os.environ.get("TUNE_TAG", "default"), "n": n, "m": m,
         "grid": acc.launch_geometry(), "ms_update": total, "ms_a": a, "ms_b": b,
         "ms_state": t["state"]["ms"] / steps, "ms_mat": t["materialise"]["ms"] / max(t["materialise"]["count"], 1),
-        "tbs_a_actual": (m + 2) * n * 8 / a / 1e9, "tbs_b_actual": (m + 5) * n * 8 / b / 1e9,
+        "lazy": lazy,
+        "tbs_a_actual": (m + (1 if lazy else 2)) * n * 8 / a / 1e9, "tbs_b_actual": (m + 4) * n * 8 / b / 1e9,
         "updates_per_s": 1e3 / total, "frac_roofline": (2 * m + 4) * n * 8 / (total * 1e-3) / 1e9 / 6554.9,
         "num_vec": acc.num_vec(),
     }
