@@ -219,19 +219,16 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from nka_b200 import NKA, comm_unique_id
+    from nka_b200 import NKA
+    from nka_b200.distributed import distributed_nka
 
     n, m = args.n, args.mvec
-    lo = (n * rank) // world
-    hi = (n * (rank + 1)) // world
-    n_local = hi - lo
-
     stream = torch.cuda.Stream()
-    acc = NKA(n_local, m, VTOL, device=local_rank, stream=stream.cuda_stream)
     if world > 1:
-        ids = [comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        acc.comm_init(world, rank, ids[0])
+        acc, lo, hi = distributed_nka(n, m, VTOL, device=local_rank, stream=stream.cuda_stream)
+    else:
+        acc, lo, hi = NKA(n, m, VTOL, device=local_rank, stream=stream.cuda_stream), 0, n
+    n_local = hi - lo
 
     # synthetic inputs, resident in HBM: a pool of mvec+3 independent vectors used round-robin.
     # accel_update overwrites f with f + (a tiny projection), so a revisited buffer is again an
@@ -322,8 +319,9 @@ def run_ours(args):
         ups = args.steps / (elapsed_ms * 1e-3)
         algo = algorithmic_bytes(n, m)
         gbs = ups * algo / 1e9
-        # dominant kernel = pass B (M+1 column reads, 3 column writes).  Its share of the
-        # algorithmic bytes: the M "v" columns + the three writes (f_out, new w, new v) = (M+3) n 8.
+        # dominant kernel = pass B (f + M Z-column reads, 3 column writes).  Its share of the
+        # algorithmic bytes: the M "v" columns + the three writes (f_out, new w, new v) = (M+3) n 8;
+        # pass A's share: the M "w" columns + f = (M+1) n 8 (it streams exactly that: lazy last column).
         kb = kt["pass_b"]
         ka = kt["pass_a"]
         algo_b = (m + 3) * n_local * 8

@@ -95,7 +95,8 @@ void nka_timing_enable (NKA, int on);
 void nka_timing_reset (NKA);
 void nka_timing_read (NKA, double ms[5], unsigned long long count[5]);
 
-/* Grid/block geometry of the two streaming kernels for the next update. */
+/* Grid/block geometry of the two streaming kernels for the next update;
+ * *threads = 10000 * (pass A block size) + (pass B block size). */
 void nka_launch_geometry (NKA, int *grid_a, int *grid_b, int *threads);
 
 const char *nka_b200_version (void);

@@ -41,7 +41,7 @@ nka_fixup_kernel(const double* __restrict__ f, const double* __restrict__ W, siz
     acc[1] = fma(x0, dl, acc[1]);
   }
   __shared__ NkaStateStage sm;
-  const bool last = nka_grid_reduce<2>(acc, partials, ticket, [&](int j, double v) {
+  const bool last = nka_grid_reduce<2, NKA_THREADS>(acc, partials, ticket, [&](int j, double v) {
     dots[(j == 0 ? 0 : NKA_MAXSLOT) + jl] = v;
   });
   if (last) {

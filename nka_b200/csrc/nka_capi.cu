@@ -37,6 +37,9 @@
 // ---------------------------------------------------------------------------
 // kernel dispatch (tables live in nka_pass_a.cu / nka_pass_b.cu)
 // ---------------------------------------------------------------------------
+#ifndef NKA_WAVES
+#define NKA_WAVES 8          // CTAs per SM = resident CTAs x NKA_WAVES
+#endif
 static bool g_tables_ready = false;
 static int g_grid_per_sm_a = 0, g_grid_per_sm_b = 0;   // 0 = occupancy-derived; env overrides for tuning
 static void ensure_tables()
@@ -170,10 +173,10 @@ struct SpanScope {
   }
 };
 
-static int grid_for(NKA st, int occ, size_t n, int V)
+static int grid_for(NKA st, int occ, size_t n, int V, int threads = NKA_THREADS)
 {
   const size_t nv = n / V;
-  size_t need = (nv + NKA_THREADS - 1) / NKA_THREADS;
+  size_t need = (nv + threads - 1) / threads;
   if (need < 1) need = 1;
   size_t full = (size_t)st->num_sms * (occ > 0 ? occ : 1);
   size_t g = need < full ? need : full;
@@ -186,8 +189,9 @@ static int occupancy_a(NKA st, int nc, int V)
   if (st->occ_a[nc][V] < 0) {
     int nb = 0;
     NKA_REQUIRE(nka_get_pass_a(nc, V) != nullptr, "pass A is not instantiated for this subspace size in this build");
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nka_get_pass_a(nc, V), NKA_THREADS, 0));
-    st->occ_a[nc][V] = g_grid_per_sm_a > 0 ? g_grid_per_sm_a : nb;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nka_get_pass_a(nc, V), NKA_THREADS_A, 0));
+    // several waves of CTAs per SM even out the tail of the grid-stride sweep (profiles/r1c sweep)
+    st->occ_a[nc][V] = g_grid_per_sm_a > 0 ? g_grid_per_sm_a : (nb > 0 ? nb : 1) * NKA_WAVES;
   }
   return st->occ_a[nc][V];
 }
@@ -197,8 +201,8 @@ static int occupancy_b(NKA st, int nz, int V)
   if (st->occ_b[nz][V] < 0) {
     int nb = 0;
     NKA_REQUIRE(nka_get_pass_b(nz, V) != nullptr, "pass B is not instantiated for this subspace size in this build");
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nka_get_pass_b(nz, V), NKA_THREADS, 0));
-    st->occ_b[nz][V] = g_grid_per_sm_b > 0 ? g_grid_per_sm_b : nb;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nka_get_pass_b(nz, V), NKA_THREADS_B, 0));
+    st->occ_b[nz][V] = g_grid_per_sm_b > 0 ? g_grid_per_sm_b : (nb > 0 ? nb : 1) * NKA_WAVES;
   }
   return st->occ_b[nz][V];
 }
@@ -254,7 +258,7 @@ extern "C" NKA nka_init_ex(size_t vlen, int mvec, double vtol, int device, void*
              poolbytes, cudaGetErrorString(e));
     nka_fail(__FILE__, __LINE__, b);
   }
-  st->max_grid = st->num_sms * 16;
+  st->max_grid = st->num_sms * 32;
   CUDA_CHECK(cudaMalloc(&st->S, sizeof(NkaDevState)));
   CUDA_CHECK(cudaMalloc(&st->dots, 2 * NKA_MAXSLOT * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&st->partials, (size_t)st->max_grid * 2 * NKA_MAXSLOT * sizeof(double)));
@@ -316,10 +320,10 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
   const int NC = may_skip ? st->mvec : L;           // columns pass A can be asked to stream
 
   if (L > 0) {
-    const int grid = grid_for(st, occupancy_a(st, NC, V), n, V);
+    const int grid = grid_for(st, occupancy_a(st, NC, V), n, V, NKA_THREADS_A);
     {
       SpanScope t(st, T_PASS_A);
-      nka_get_pass_a(NC, V)<<<grid, NKA_THREADS, 0, st->stream>>>(f, st->W, st->ld, n, st->S, st->partials, st->ticket,
+      nka_get_pass_a(NC, V)<<<grid, NKA_THREADS_A, 0, st->stream>>>(f, st->W, st->ld, n, st->S, st->partials, st->ticket,
                                                             st->dots, single ? 1 : 0);
       CUDA_CHECK(cudaGetLastError());
       st->launches += 1;
@@ -351,9 +355,9 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
   }
   {
     const int nz = nz_expected(st);
-    const int grid = grid_for(st, occupancy_b(st, nz, V), n, V);
+    const int grid = grid_for(st, occupancy_b(st, nz, V), n, V, NKA_THREADS_B);
     SpanScope t(st, T_PASS_B);
-    nka_get_pass_b(nz, V)<<<grid, NKA_THREADS, 0, st->stream>>>(f, st->W, st->Z, st->ld, n, st->S);
+    nka_get_pass_b(nz, V)<<<grid, NKA_THREADS_B, 0, st->stream>>>(f, st->W, st->Z, st->ld, n, st->S);
     CUDA_CHECK(cudaGetLastError());
     st->launches += 1;
   }
@@ -529,10 +533,10 @@ extern "C" void nka_launch_geometry(NKA st, int* grid_a, int* grid_b, int* threa
   const int L = st->ub_len;
   const bool may_skip = st->comm == nullptr && st->lazy && st->pending && L == st->mvec + 1;
   const int NC = may_skip ? st->mvec : L;
-  if (grid_a) *grid_a = L > 0 ? grid_for(st, occupancy_a(st, NC, 2), st->vlen, 2) : 0;
+  if (grid_a) *grid_a = L > 0 ? grid_for(st, occupancy_a(st, NC, 2), st->vlen, 2, NKA_THREADS_A) : 0;
   const int nz = nz_expected(st);
-  if (grid_b) *grid_b = grid_for(st, occupancy_b(st, nz, 2), st->vlen, 2);
-  if (threads) *threads = NKA_THREADS;
+  if (grid_b) *grid_b = grid_for(st, occupancy_b(st, nz, 2), st->vlen, 2, NKA_THREADS_B);
+  if (threads) *threads = NKA_THREADS_A * 10000 + NKA_THREADS_B;
 }
 
 extern "C" const char* nka_b200_version(void) { return NKA_VERSION; }

@@ -25,9 +25,17 @@
 
 #include "nka_state.h"
 
-// Tunables (profiles/ records the sweeps that picked the defaults).
+// Tunables.  Defaults picked by the sweeps recorded in profiles/r1*_tune_sweep.jsonl
+// (n = 2^28, mvec = 10 on B200): plain ld.global.nc / st.global beat the .cs streaming
+// hints by 10 % in pass B; 256 threads suit the register-heavy pass A, 512 pass B.
 #ifndef NKA_THREADS
-#define NKA_THREADS 256
+#define NKA_THREADS 256      // fix-up / materialise kernels and the default for both passes
+#endif
+#ifndef NKA_THREADS_A
+#define NKA_THREADS_A NKA_THREADS
+#endif
+#ifndef NKA_THREADS_B
+#define NKA_THREADS_B 512
 #endif
 #ifndef NKA_MINB_A
 #define NKA_MINB_A 1      // __launch_bounds__ min CTAs/SM for pass A
@@ -36,10 +44,10 @@
 #define NKA_MINB_B 1
 #endif
 #ifndef NKA_STORE_STREAM
-#define NKA_STORE_STREAM 1   // 1: st.global.cs for the cached columns, 0: default write-back policy
+#define NKA_STORE_STREAM 0   // 1: st.global.cs for the cached columns, 0: default write-back policy
 #endif
 #ifndef NKA_LOAD_STREAM
-#define NKA_LOAD_STREAM 1    // 1: ld.global.cs (evict-first) for subspace columns, 0: ld.global.nc
+#define NKA_LOAD_STREAM 0    // 0: ld.global.nc, 1: ld.global.cs (evict-first), 2/3: L1::no_allocate variants
 #endif
 #define NKA_STATE_THREADS 128
 
@@ -52,12 +60,23 @@ template <int V> struct Vec;
 template <> struct Vec<2> {
   double x, y;
   static __device__ __forceinline__ Vec ld(const double* p, size_t i) {
-#if NKA_LOAD_STREAM
+#if NKA_LOAD_STREAM == 1
     const double2 t = __ldcs(reinterpret_cast<const double2*>(p) + i);
+    return {t.x, t.y};
+#elif NKA_LOAD_STREAM == 2
+    double a, b;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v2.f64 {%0,%1}, [%2];"
+                 : "=d"(a), "=d"(b) : "l"(reinterpret_cast<const double2*>(p) + i));
+    return {a, b};
+#elif NKA_LOAD_STREAM == 3
+    double a, b;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0,%1}, [%2];"
+                 : "=d"(a), "=d"(b) : "l"(reinterpret_cast<const double2*>(p) + i));
+    return {a, b};
 #else
     const double2 t = __ldg(reinterpret_cast<const double2*>(p) + i);
-#endif
     return {t.x, t.y};
+#endif
   }
   static __device__ __forceinline__ Vec ld_keep(const double* p, size_t i) {
     const double2 t = __ldg(reinterpret_cast<const double2*>(p) + i);
@@ -85,10 +104,22 @@ template <> struct Vec<2> {
 };
 template <> struct Vec<1> {
   double x;
-  static __device__ __forceinline__ Vec ld(const double* p, size_t i) { return {__ldcs(p + i)}; }
+  static __device__ __forceinline__ Vec ld(const double* p, size_t i) {
+#if NKA_LOAD_STREAM == 1
+    return {__ldcs(p + i)};
+#else
+    return {__ldg(p + i)};
+#endif
+  }
   static __device__ __forceinline__ Vec ld_keep(const double* p, size_t i) { return {__ldg(p + i)}; }
   static __device__ __forceinline__ Vec ld_plain(const double* p, size_t i) { return {p[i]}; }
-  __device__ __forceinline__ void st_stream(double* p, size_t i) const { __stcs(p + i, x); }
+  __device__ __forceinline__ void st_stream(double* p, size_t i) const {
+#if NKA_STORE_STREAM
+    __stcs(p + i, x);
+#else
+    p[i] = x;
+#endif
+  }
   __device__ __forceinline__ void st(double* p, size_t i) const { p[i] = x; }
   static __device__ __forceinline__ Vec zero() { return {0.0}; }
   __device__ __forceinline__ Vec operator-(const Vec& o) const { return {x - o.x}; }
@@ -111,11 +142,11 @@ __device__ __forceinline__ double nka_warp_sum(double v)
 // a given grid).  Returns true in every thread of that last CTA, after out(j, v)
 // has been called for each j.  Atomic-free except for the ticket.
 // ---------------------------------------------------------------------------
-template <int K, typename Out>
+template <int K, int THREADS, typename Out>
 __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* __restrict__ partials,
                                                 unsigned* __restrict__ ticket, Out out)
 {
-  __shared__ double red[NKA_THREADS / 32][K];
+  __shared__ double red[THREADS / 32][K];
   __shared__ bool is_last;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -127,7 +158,7 @@ __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* 
   if (threadIdx.x < K) {
     double v = 0.0;
 #pragma unroll
-    for (int w = 0; w < NKA_THREADS / 32; ++w) v += red[w][threadIdx.x];
+    for (int w = 0; w < THREADS / 32; ++w) v += red[w][threadIdx.x];
     partials[(size_t)blockIdx.x * K + threadIdx.x] = v;
   }
   __threadfence();
@@ -139,7 +170,7 @@ __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* 
   __syncthreads();
   if (!is_last) return false;
   __threadfence();
-  for (int j = warp; j < K; j += NKA_THREADS / 32) {
+  for (int j = warp; j < K; j += THREADS / 32) {
     double v = 0.0;
     for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(&partials[(size_t)b * K + j]);
     v = nka_warp_sum(v);
@@ -231,7 +262,7 @@ __device__ __forceinline__ void nka_pass_a_elem(const double* __restrict__ f, co
 }
 
 template <int NC, int V>
-__global__ void __launch_bounds__(NKA_THREADS, NKA_MINB_A)
+__global__ void __launch_bounds__(NKA_THREADS_A, NKA_MINB_A)
 nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld, size_t n,
            NkaDevState* __restrict__ S, double* __restrict__ partials, unsigned* __restrict__ ticket,
            double* __restrict__ dots, int fuse_state)
@@ -247,8 +278,8 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
   for (int j = 0; j < 2 * NC; ++j) acc[j] = 0.0;
 
   const size_t nv = n / V;
-  const size_t stride = (size_t)gridDim.x * NKA_THREADS;
-  const size_t start = (size_t)blockIdx.x * NKA_THREADS + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * NKA_THREADS_A;
+  const size_t start = (size_t)blockIdx.x * NKA_THREADS_A + threadIdx.x;
   const unsigned allbits = NC >= 32 ? 0xffffffffu : ((1u << NC) - 1u);
   const bool full = (ncol == NC) && ((submask & allbits) == allbits);
   if (full) {
@@ -259,7 +290,7 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
   if (V == 2 && (n & 1) && start == 0) nka_pass_a_elem<NC, 1, false>(f, wcol, n - 1, ncol, submask, acc);
 
   __shared__ NkaStateStage sm;     // used by the last CTA only
-  const bool last = nka_grid_reduce<2 * NC>(acc, partials, ticket, [&](int j, double v) {
+  const bool last = nka_grid_reduce<2 * NC, NKA_THREADS_A>(acc, partials, ticket, [&](int j, double v) {
     const int at = (j < NC) ? j : (NKA_MAXSLOT + (j - NC));
     dots[at] = v;
     sm.dots[at] = v;
@@ -327,7 +358,7 @@ __device__ __forceinline__ void nka_pass_b_elem(double* __restrict__ f, double* 
 }
 
 template <int NZ, int V>
-__global__ void __launch_bounds__(NKA_THREADS, NKA_MINB_B)
+__global__ void __launch_bounds__(NKA_THREADS_B, NKA_MINB_B)
 nka_pass_b(double* __restrict__ f, double* W, double* Z, size_t ld, size_t n, const NkaDevState* __restrict__ S)
 {
   constexpr int NZA = NZ > 0 ? NZ : 1;
@@ -346,8 +377,8 @@ nka_pass_b(double* __restrict__ f, double* W, double* Z, size_t ld, size_t n, co
     coefY[k] = on ? B->coefY[k] : 0.0;
   }
   const size_t nv = n / V;
-  const size_t stride = (size_t)gridDim.x * NKA_THREADS;
-  const size_t start = (size_t)blockIdx.x * NKA_THREADS + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * NKA_THREADS_B;
+  const size_t start = (size_t)blockIdx.x * NKA_THREADS_B + threadIdx.x;
   const bool full = (nz == NZ) && has_pair && write_f && (S->planM.n == 0);
   if (full) {
     for (size_t i = start; i < nv; i += stride)

@@ -186,15 +186,29 @@ def test_large_n_against_long_double_arbiter():
 
 
 def test_example_replay_open_loop():
-    """The example's own 26-call f-sequence (n = 2500, mvec = 5, vtol = 0.01): every correction
-    within 1e-12, num_vec 0,1,2,3,4,5,5,...; pins src-F95/reference_output:5-31 through the oracle."""
+    """The example's own 26-call f-sequence (n = 2500, mvec = 5, vtol = 0.01), replayed open loop.
+    Every correction is within 1e-12 of the reference algorithm evaluated with long-double dot
+    products, and num_vec is 0,1,2,3,4,5,5,...  Against the unmodified (serial-sum) reference the
+    distance is bounded by that code's own summation noise: on this ill-conditioned sequence its
+    serial and long-double runs differ by up to 1.2e-11, so 1e-12 against it is not attainable
+    by ANY implementation that does not replicate its left-to-right summation order."""
     from nka_b200 import NKA
     res = api.example_solve(mvec=5, record=True)
+    T = res["iters"]
+    arb = api.OracleNKA(2500, 5, 0.01, dotmode=1)
+    arbiter = []
+    for t in range(T):
+        g = res["fseq"][t].copy()
+        arb.accel_update(g)
+        arbiter.append(g)
+    scales, tols = S.tolerances(list(res["gseq"]), arbiter, list(res["fseq"]))
     acc = NKA(2500, 5, 0.01)
-    for t in range(res["iters"]):
+    for t in range(T):
         d = _dev(res["fseq"][t])
         acc.accel_update(d)
-        assert _rel(d.cpu().numpy(), res["gseq"][t]) <= 1e-12, t
+        got = d.cpu().numpy()
+        assert _rel(got, arbiter[t]) <= 1e-12, t
+        assert np.linalg.norm(got - res["gseq"][t]) / scales[t] <= tols[t], t
         assert acc.num_vec() == res["nvec"][t]
     acc.delete()
 

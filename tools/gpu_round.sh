@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for what in "$@"; do
 case $what in
 tests)
-  timeout 1500 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest_rc=$?" >> gpurun_out/pytest_gpu_$tag.log
+  timeout 1500 python -m pytest tests -m gpu -q --maxfail=8 > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest_rc=$?" >> gpurun_out/pytest_gpu_$tag.log
   tail -4 gpurun_out/pytest_gpu_$tag.log
   timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$tag.log 2>&1; echo "smoke_rc=$?" >> gpurun_out/smoke_$tag.log
   tail -2 gpurun_out/smoke_$tag.log ;;
