@@ -68,6 +68,34 @@ int nka_comm_init (NKA, int nranks, int rank, const void *id128);
 /* Alternatively adopt an existing ncclComm_t (not owned). */
 void nka_comm_adopt (NKA, void *nccl_comm, int nranks, int rank);
 
+/* ---- device vectors: the operations of the reference's abstract `vector` ---- */
+/* What a concrete gpu_vector extension of src-F08-vector/vector_class.F90:90-109
+ * needs.  Expression order follows grid_vector (grid_vector_type.F90:108-197).
+ * dot/norm2 return the value to the host (they synchronise the vector's stream)
+ * and, with a communicator, sum over all ranks' slabs. */
+typedef struct nka_vec *NKAVEC;
+NKAVEC nka_vec_create (size_t n, int device, void *stream);   /* contents undefined, like allocate() */
+NKAVEC nka_vec_clone (NKAVEC src);                            /* allocate(clone, source=src): :86-97 */
+void nka_vec_destroy (NKAVEC);
+size_t nka_vec_size (NKAVEC);
+double *nka_vec_data (NKAVEC);                                /* device pointer */
+void nka_vec_set_host (NKAVEC, const double *host);           /* host -> device, synchronous */
+void nka_vec_get_host (NKAVEC, double *host);                 /* device -> host, synchronous */
+void nka_vec_copy (NKAVEC dst, NKAVEC src);                   /* copy_   :99-106 */
+void nka_vec_setval (NKAVEC, double val);                     /* setval  :108-112 */
+void nka_vec_scale (NKAVEC, double a);                        /* scale   :114-118 */
+void nka_vec_update1 (NKAVEC y, double a, NKAVEC x);                       /* y = a*x + y        :121-129 */
+void nka_vec_update2 (NKAVEC y, double a, NKAVEC x, double b);             /* y = a*x + b*y      :132-140 */
+void nka_vec_update3 (NKAVEC z, double a, NKAVEC x, double b, NKAVEC y);   /* z = a*x + b*y + z  :143-154 */
+void nka_vec_update4 (NKAVEC z, double a, NKAVEC x, double b, NKAVEC y, double c); /* z = a*x+b*y+c*z :157-168 */
+double nka_vec_dot (NKAVEC x, NKAVEC y);                      /* dot_    :170-184 */
+double nka_vec_norm2 (NKAVEC x);                              /* norm2   :186-197 */
+int nka_vec_comm_init (NKAVEC, int nranks, int rank, const void *id128); /* clones share it */
+/* The vector flavour's init(vec, mvec) and accel_update(f):
+ * src-F08-vector/nka_type.F90:175-188, :219-222. */
+NKA nka_init_like (NKAVEC proto, int mvec, double vtol);
+void nka_accel_update_vec (NKA, NKAVEC f);
+
 /* ---- introspection (tests, benchmarks; never on the hot path) ---------- */
 
 typedef struct nka_state_view {

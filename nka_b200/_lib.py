@@ -51,6 +51,25 @@ SYMBOLS = {
     "nka_comm_unique_id": (C.c_int, [C.c_void_p]),
     "nka_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "nka_comm_adopt": (None, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "nka_vec_create": (C.c_void_p, [C.c_size_t, C.c_int, C.c_void_p]),
+    "nka_vec_clone": (C.c_void_p, [C.c_void_p]),
+    "nka_vec_destroy": (None, [C.c_void_p]),
+    "nka_vec_size": (C.c_size_t, [C.c_void_p]),
+    "nka_vec_data": (C.c_void_p, [C.c_void_p]),
+    "nka_vec_set_host": (None, [C.c_void_p, C.c_void_p]),
+    "nka_vec_get_host": (None, [C.c_void_p, C.c_void_p]),
+    "nka_vec_copy": (None, [C.c_void_p, C.c_void_p]),
+    "nka_vec_setval": (None, [C.c_void_p, C.c_double]),
+    "nka_vec_scale": (None, [C.c_void_p, C.c_double]),
+    "nka_vec_update1": (None, [C.c_void_p, C.c_double, C.c_void_p]),
+    "nka_vec_update2": (None, [C.c_void_p, C.c_double, C.c_void_p, C.c_double]),
+    "nka_vec_update3": (None, [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p]),
+    "nka_vec_update4": (None, [C.c_void_p, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_double]),
+    "nka_vec_dot": (C.c_double, [C.c_void_p, C.c_void_p]),
+    "nka_vec_norm2": (C.c_double, [C.c_void_p]),
+    "nka_vec_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "nka_init_like": (C.c_void_p, [C.c_void_p, C.c_int, C.c_double]),
+    "nka_accel_update_vec": (None, [C.c_void_p, C.c_void_p]),
     "nka_get_state": (None, [C.c_void_p, C.POINTER(StateView)]),
     "nka_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "nka_timing_enable": (None, [C.c_void_p, C.c_int]),

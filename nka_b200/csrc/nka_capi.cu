@@ -15,12 +15,13 @@
 #include <vector>
 
 #include "../../include/nka_b200.h"
+#include "nka_internal.h"
 #include "nka_dispatch.h"
 #include "nka_aux_kernels.cuh"
 
 #define NKA_VERSION "nka_b200 0.1 (sm_100a)"
 
-[[noreturn]] static void nka_fail(const char* file, int line, const char* msg)
+[[noreturn]] void nka_fail(const char* file, int line, const char* msg)
 {
   // the reference's convention: "Assertion failed at file:line" then stop
   // (src-F08/f90_assert.F90:37-47); we abort so the failure cannot be ignored.
@@ -28,11 +29,6 @@
   fflush(stderr);
   abort();
 }
-
-#define NKA_REQUIRE(cond, msg) do { if (!(cond)) nka_fail(__FILE__, __LINE__, msg); } while (0)
-#define CUDA_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                 \
-    char b_[256]; snprintf(b_, sizeof b_, "%s failed: %s", #call, cudaGetErrorString(e_));      \
-    nka_fail(__FILE__, __LINE__, b_); } } while (0)
 
 // ---------------------------------------------------------------------------
 // kernel dispatch (tables live in nka_pass_a.cu / nka_pass_b.cu)
@@ -54,18 +50,9 @@ static void ensure_tables()
 // ---------------------------------------------------------------------------
 // NCCL, resolved at run time so single-GPU users need no NCCL at all
 // ---------------------------------------------------------------------------
-struct Id128 { char bytes[128]; };
-struct NcclApi {
-  void* lib = nullptr;
-  int (*GetUniqueId)(void*) = nullptr;
-  int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ Id128, int) = nullptr;
-  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
-  int (*CommDestroy)(void*) = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
-};
-static NcclApi g_nccl;
+NkaNcclApi g_nccl;
 
-static bool nccl_load()
+bool nka_nccl_load()
 {
   if (g_nccl.lib) return true;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -75,14 +62,22 @@ static bool nccl_load()
   }
   if (!g_nccl.lib) return false;
   g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
-  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+  g_nccl.CommInitRank = (int (*)(void**, int, NkaId128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
   return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
 }
-static const int kNcclFloat64 = 8;   // ncclDouble
-static const int kNcclSum = 0;       // ncclSum
+
+NkaComm* nka_comm_retain(NkaComm* c) { if (c) c->refs += 1; return c; }
+void nka_comm_release(NkaComm* c)
+{
+  if (!c) return;
+  if (--c->refs == 0) {
+    if (c->comm && c->owned && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+  }
+}
 
 // ---------------------------------------------------------------------------
 // the handle
@@ -112,9 +107,7 @@ struct nka_state {
   int ub_len = 0;
   bool lazy = true;             // skip the doomed oldest column in pass A (single GPU only)
   // distributed
-  void* comm = nullptr;
-  bool own_comm = false;
-  int nranks = 1, rank = 0;
+  NkaComm* comm = nullptr;
   // accounting
   unsigned long long launches = 0;
   bool timing = false;
@@ -124,15 +117,6 @@ struct nka_state {
   unsigned long long t_cnt[T_NKIND] = {0, 0, 0, 0, 0};
   int occ_a[NKA_MAXSLOT + 1][3];
   int occ_b[NKA_MAXSLOT + 1][3];
-};
-
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    CUDA_CHECK(cudaGetDevice(&prev));
-    if (prev != dev) CUDA_CHECK(cudaSetDevice(dev)); else prev = -1;
-  }
-  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
 static cudaEvent_t get_event(NKA st)
@@ -297,7 +281,7 @@ extern "C" void nka_delete(NKA st)
   cudaStreamSynchronize(st->stream);
   for (const TimedSpan& sp : st->spans) { cudaEventDestroy(sp.beg); cudaEventDestroy(sp.end); }
   for (cudaEvent_t ev : st->free_events) cudaEventDestroy(ev);
-  if (st->comm && st->own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(st->comm);
+  nka_comm_release(st->comm);
   cudaFree(st->W); cudaFree(st->Z); cudaFree(st->S); cudaFree(st->dots);
   cudaFree(st->partials); cudaFree(st->ticket); cudaFree(st->fstage);
   if (st->own_stream) cudaStreamDestroy(st->stream);
@@ -331,7 +315,7 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
     if (!single) {
       {
         SpanScope t(st, T_COMM);
-        const int rc = g_nccl.AllReduce(st->dots, st->dots, 2 * NKA_MAXSLOT, kNcclFloat64, kNcclSum, st->comm, st->stream);
+        const int rc = g_nccl.AllReduce(st->dots, st->dots, 2 * NKA_MAXSLOT, kNcclFloat64, kNcclSum, st->comm->comm, st->stream);
         if (rc != 0) nka_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclAllReduce failed");
       }
       SpanScope t(st, T_STATE);
@@ -546,31 +530,47 @@ extern "C" const char* nka_b200_version(void) { return NKA_VERSION; }
 // ---------------------------------------------------------------------------
 extern "C" int nka_comm_unique_id(void* id128)
 {
-  if (!nccl_load()) return -1;
+  if (!nka_nccl_load()) return -1;
   return g_nccl.GetUniqueId(id128);
+}
+
+static void attach_comm(NKA st, NkaComm* c)
+{
+  nka_comm_release(st->comm);
+  st->comm = c;
+  set_lazy(st, false);     // a conditional second all-reduce is not worth it: every rank streams all columns
 }
 
 extern "C" int nka_comm_init(NKA st, int nranks, int rank, const void* id128)
 {
   NKA_REQUIRE(st != NULL && id128 != NULL, "nka_comm_init: null argument");
   NKA_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "nka_comm_init: bad rank/nranks");
-  if (!nccl_load()) return -1;
+  if (!nka_nccl_load()) return -1;
   DeviceGuard guard(st->device);
-  Id128 id;
+  NkaId128 id;
   memcpy(id.bytes, id128, sizeof id.bytes);
   void* comm = nullptr;
   const int rc = g_nccl.CommInitRank(&comm, nranks, id, rank);
   if (rc != 0) return rc;
-  st->comm = comm; st->own_comm = true; st->nranks = nranks; st->rank = rank;
-  set_lazy(st, false);     // a conditional second all-reduce is not worth it: every rank streams all columns
+  NkaComm* c = new NkaComm();
+  c->comm = comm; c->owned = true; c->nranks = nranks; c->rank = rank;
+  attach_comm(st, c);
   return 0;
 }
 
 extern "C" void nka_comm_adopt(NKA st, void* nccl_comm, int nranks, int rank)
 {
   NKA_REQUIRE(st != NULL, "nka_comm_adopt: null handle");
-  NKA_REQUIRE(nccl_load(), "nka_comm_adopt: libnccl.so.2 not found");
-  st->comm = nccl_comm; st->own_comm = false; st->nranks = nranks; st->rank = rank;
+  NKA_REQUIRE(nka_nccl_load(), "nka_comm_adopt: libnccl.so.2 not found");
   DeviceGuard guard(st->device);
-  set_lazy(st, false);
+  NkaComm* c = new NkaComm();
+  c->comm = nccl_comm; c->owned = false; c->nranks = nranks; c->rank = rank;
+  attach_comm(st, c);
+}
+
+// used by nka_vec.cu: an accelerator shaped like a vector shares that vector's communicator
+void nka_attach_shared_comm(NKA st, NkaComm* c)
+{
+  DeviceGuard guard(st->device);
+  attach_comm(st, nka_comm_retain(c));
 }

@@ -1,0 +1,48 @@
+// nka_internal.h -- declarations shared by the translation units of libnka_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+[[noreturn]] void nka_fail(const char* file, int line, const char* msg);
+
+#define NKA_REQUIRE(cond, msg) do { if (!(cond)) nka_fail(__FILE__, __LINE__, msg); } while (0)
+#define CUDA_CHECK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) {                 \
+    char b_[256]; snprintf(b_, sizeof b_, "%s failed: %s", #call, cudaGetErrorString(e_));      \
+    nka_fail(__FILE__, __LINE__, b_); } } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    CUDA_CHECK(cudaGetDevice(&prev));
+    if (prev != dev) CUDA_CHECK(cudaSetDevice(dev)); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// NCCL, resolved at run time (dlopen) so single-GPU users need no NCCL at all.
+struct NkaId128 { char bytes[128]; };
+struct NkaNcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NkaId128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+extern NkaNcclApi g_nccl;
+bool nka_nccl_load();
+static const int kNcclFloat64 = 8;   // ncclDouble
+static const int kNcclSum = 0;       // ncclSum
+
+// A reference-counted communicator shared by vectors cloned from one another and by the
+// accelerator created from them.
+struct NkaComm {
+  void* comm = nullptr;
+  bool owned = false;
+  int nranks = 1, rank = 0;
+  int refs = 1;
+};
+NkaComm* nka_comm_retain(NkaComm* c);
+void nka_comm_release(NkaComm* c);

@@ -19,6 +19,26 @@ ncu)
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:nka_pass -s 30 -c 4 -f -o gpurun_out/prof_$tag \
      python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_$tag.log 2>&1
   ls -la gpurun_out/prof_$tag.ncu-rep ;;
+multi)
+  ng=${NGPUS:-2}
+  timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q > gpurun_out/pytest_multi_$tag.log 2>&1; echo "pytest_multi_rc=$?" >> gpurun_out/pytest_multi_$tag.log
+  tail -3 gpurun_out/pytest_multi_$tag.log
+  for g in 1 $ng; do
+    if [ $g = 1 ]; then
+      timeout 600 python bench.py --gpus 1 --no-cpu-baseline > gpurun_out/bench_g1_$tag.json 2> gpurun_out/bench_g1_$tag.err
+    else
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $g --master-addr 127.0.0.1 --master-port 29511 \
+        bench.py --gpus $g > gpurun_out/bench_g${g}_$tag.json 2> gpurun_out/bench_g${g}_$tag.err
+    fi
+    echo "bench g=$g rc=$?"; tail -2 gpurun_out/bench_g${g}_$tag.err
+    python - <<PY
+import json
+try:
+    d=json.loads(open("gpurun_out/bench_g${g}_$tag.json").read().strip().splitlines()[-1])
+    print("g=$g value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"] and d["e2e"]["value"], "kern", {k:(v.get("avg_ms") if isinstance(v,dict) else v) for k,v in d["kernels"].items() if k!="geometry"})
+except Exception as e: print("parse failed", e)
+PY
+  done ;;
 tune)
   : > gpurun_out/tune_$tag.jsonl
   for lib in ${TUNE_LIBS:-default t256_b2 t512_b1 t256_b1_st0 t512_b1_st0 t512_b1_ld0 t1024_b1}; do
