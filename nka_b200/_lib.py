@@ -77,6 +77,22 @@ SYMBOLS = {
     "nka_timing_read": (None, [C.c_void_p, _dp, C.POINTER(C.c_ulonglong)]),
     "nka_launch_geometry": (None, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "nka_b200_version": (C.c_char_p, []),
+    # include/nka_example.h
+    "nka_system_init": (C.c_void_p, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]),
+    "nka_system_delete": (None, [C.c_void_p]),
+    "nka_system_size": (C.c_size_t, [C.c_void_p]),
+    "nka_system_stream": (C.c_void_p, [C.c_void_p]),
+    "nka_system_field": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "nka_system_index": (C.c_size_t, [C.c_void_p, C.c_int, C.c_int]),
+    "nka_system_set_field": (None, [C.c_void_p, C.c_int, C.c_void_p]),
+    "nka_system_get_field": (None, [C.c_void_p, C.c_int, C.c_void_p]),
+    "nka_system_residual": (C.c_double, [C.c_void_p, C.c_int]),
+    "nka_system_pc_ssor": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "nka_example_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double,
+                                    _dp, C.POINTER(C.c_int)]),
+    "nka_system_timing_enable": (None, [C.c_void_p, C.c_int]),
+    "nka_system_timing_read": (None, [C.c_void_p, _dp, C.POINTER(C.c_ulonglong)]),
+    "nka_system_launch_count": (C.c_ulonglong, [C.c_void_p]),
 }
 
 _lib = None

@@ -1,0 +1,621 @@
+// nka_example.cu -- the reference example's discrete system and Picard solver on the device
+// (declarations and the reference lines being replaced: include/nka_example.h).
+//
+// Kernels (all sm_100a, fp64, none of them GEMM-shaped):
+//   ex_residual_kernel   u <- u - z (optional), face coefficients ax/ay/ac from u, residual r,
+//                        and sum r^2 in one stencil sweep (HBM bound; deterministic reduction).
+//                        Replaces update_system + residual + `u = u - r` + norm2:
+//                        src-F08/nka_example.F90:103-145, :248-250.
+//   ex_ssor_sweep<DIR>   one Gauss-Seidel/SOR sweep in the reference's lexicographic order
+//                        (DIR=+1 forward, -1 backward), src-F08/nka_example.F90:159-175, as a
+//                        pipelined anti-diagonal wavefront: one thread per grid column, one warp
+//                        per strip of 32 columns, neighbouring strips hand over their edge values
+//                        through a flag-in-data channel in L2.  Latency bound: the chain
+//                        z(j-1,k) -> z(j,k) is serial by definition of the method.
+//   ex_permute_kernel    natural order <-> wavefront-major (I/O only).
+//
+// Every cell is computed with the reference's operand order and without fma contraction
+// (__dmul_rn/__dadd_rn/__ddiv_rn), from the same neighbour values the serial loops would use,
+// so residual and SSOR are BIT-IDENTICAL to the CPU code (tests/test_gpu_example.py).
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/nka_b200.h"
+#include "../../include/nka_example.h"
+#include "nka_internal.h"
+
+#if defined(__CUDACC__)
+#define EX_HD __host__ __device__ __forceinline__
+#else
+#define EX_HD inline
+#endif
+
+// ---------------------------------------------------------------------------
+// wavefront-major geometry: diagonal t = j + k holds cells j = jmin(t)..jmax(t)
+// ---------------------------------------------------------------------------
+EX_HD long long wf_off(int t, int nx, int ny)          // cells on diagonals < t
+{
+  const long long m = nx < ny ? nx : ny, M = nx < ny ? ny : nx;
+  if (t <= m) return (long long)t * (t + 1) / 2;
+  if (t <= M) return m * (m + 1) / 2 + ((long long)t - m) * m;
+  const long long r = (long long)nx + ny - 1 - t;
+  return (long long)nx * ny - r * (r + 1) / 2;
+}
+EX_HD long long wf_base(int t, int nx, int ny)         // index of cell (j, t-j) is wf_base(t) + j
+{
+  const int jm = t - (ny - 1);
+  return wf_off(t, nx, ny) - (jm > 0 ? jm : 0);
+}
+
+// ---------------------------------------------------------------------------
+// residual
+// ---------------------------------------------------------------------------
+#define EX_RES_THREADS 256
+
+struct ResParams {
+  int nx, ny;
+  const double* U;       // current solution
+  const double* Zc;      // update to subtract first (nullptr: none)
+  double* Unew;          // receives u - z when Zc != nullptr
+  double *R, *AXL, *AYD, *AC, *AXR, *AYT;
+  double a, fx, fy, q;
+  double* partials;      // one per block
+  unsigned* ticket;
+  double* sumsq;         // result
+};
+
+__device__ __forceinline__ double ex_warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P)
+{
+  const int nx = P.nx, ny = P.ny;
+  const int t = blockIdx.x;
+  const int jmin = t - (ny - 1) > 0 ? t - (ny - 1) : 0;
+  const int jmax = t < nx - 1 ? t : nx - 1;
+  const int p = blockIdx.y * EX_RES_THREADS + threadIdx.x;
+  double rr = 0.0;
+  if (jmin + p <= jmax) {
+    const int j = jmin + p, k = t - j;
+    const long long c = wf_base(t, nx, ny) + j;
+    const long long bm = wf_base(t - 1, nx, ny), bp = wf_base(t + 1, nx, ny);
+    const bool hl = j > 0, hr = j + 1 < nx, hd = k > 0, hu = k + 1 < ny;
+    const double* __restrict__ U = P.U;
+    const double* __restrict__ Zc = P.Zc;
+    auto val = [&](long long i) {
+      const double u = __ldg(U + i);
+      return Zc ? __dsub_rn(u, __ldg(Zc + i)) : u;                 // u = u - r : F08 :248
+    };
+    const double uc = val(c);
+    const double ul = hl ? val(bm + j - 1) : 0.0, ud = hd ? val(bm + j) : 0.0;
+    const double ur = hr ? val(bp + j + 1) : 0.0, uu = hu ? val(bp + j) : 0.0;
+    // update_system (:122-145): t = 1/(a+u); each face sums the t*h^2 of its (one or two) cells
+    // in cell order (left/lower cell first), then ax = 2/ax.
+    const double tc = __ddiv_rn(1.0, __dadd_rn(P.a, uc));
+    const double txc = __dmul_rn(tc, P.fx), tyc = __dmul_rn(tc, P.fy);
+    double sxl = txc, sxr = txc, syd = tyc, syu = tyc;
+    if (hl) sxl = __dadd_rn(__dmul_rn(__ddiv_rn(1.0, __dadd_rn(P.a, ul)), P.fx), txc);
+    if (hr) sxr = __dadd_rn(txc, __dmul_rn(__ddiv_rn(1.0, __dadd_rn(P.a, ur)), P.fx));
+    if (hd) syd = __dadd_rn(__dmul_rn(__ddiv_rn(1.0, __dadd_rn(P.a, ud)), P.fy), tyc);
+    if (hu) syu = __dadd_rn(tyc, __dmul_rn(__ddiv_rn(1.0, __dadd_rn(P.a, uu)), P.fy));
+    const double axl = __ddiv_rn(2.0, sxl), axr = __ddiv_rn(2.0, sxr);
+    const double ayd = __ddiv_rn(2.0, syd), ayu = __ddiv_rn(2.0, syu);
+    const double ac = __dadd_rn(__dadd_rn(__dadd_rn(axl, axr), ayd), ayu);                   // :142
+    // residual (:115-117), left to right
+    double r = __dmul_rn(ac, uc);
+    r = __dsub_rn(r, __dmul_rn(axl, ul));
+    r = __dsub_rn(r, __dmul_rn(axr, ur));
+    r = __dsub_rn(r, __dmul_rn(ayd, ud));
+    r = __dsub_rn(r, __dmul_rn(ayu, uu));
+    r = __dsub_rn(r, P.q);
+    P.R[c] = r; P.AXL[c] = axl; P.AYD[c] = ayd; P.AC[c] = ac;
+    if (Zc) P.Unew[c] = uc;
+    if (!hr) P.AXR[k] = axr;
+    if (!hu) P.AYT[j] = ayu;
+    rr = r * r;
+  }
+  // deterministic two-stage sum of r^2: warp tree, fixed-order across warps, one partial per
+  // block, the last block (ticket) folds all partials in a fixed order
+  __shared__ double red[EX_RES_THREADS / 32];
+  __shared__ bool is_last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  rr = ex_warp_sum(rr);
+  if (lane == 0) red[warp] = rr;
+  __syncthreads();
+  const unsigned nblk = gridDim.x * gridDim.y;
+  const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+  if (threadIdx.x == 0) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < EX_RES_THREADS / 32; ++w) v += red[w];
+    P.partials[bid] = v;
+    __threadfence();
+    is_last = (atomicAdd(P.ticket, 1u) == nblk - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double v = 0.0;
+  for (unsigned b = threadIdx.x; b < nblk; b += EX_RES_THREADS) v += __ldcg(P.partials + b);
+  v = ex_warp_sum(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < EX_RES_THREADS / 32; ++w) s += red[w];
+    *P.sumsq = s;
+    *P.ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// natural order <-> wavefront-major
+// ---------------------------------------------------------------------------
+__global__ void ex_permute_kernel(double* __restrict__ dst, const double* __restrict__ src, int nx, int ny, int to_wavefront)
+{
+  const size_t n = (size_t)nx * ny;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int j = (int)(i % nx), k = (int)(i / nx);
+    const long long w = wf_base(j + k, nx, ny) + j;
+    if (to_wavefront) dst[w] = src[i];
+    else dst[i] = src[w];
+  }
+}
+
+__global__ void ex_fill_u64(unsigned long long* p, size_t n, unsigned long long v)
+{
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------
+// SSOR sweep
+// ---------------------------------------------------------------------------
+#ifndef EX_SSOR_WARPS
+#define EX_SSOR_WARPS 8          // strips (warps) per CTA
+#endif
+#ifndef EX_SSOR_RING
+#define EX_SSOR_RING 8           // own-cell operands are loaded RING-1 steps ahead of use
+#endif
+#ifndef EX_SSOR_DB
+#define EX_SSOR_DB 3             // edge values from the neighbouring strip are polled DB steps ahead
+#endif
+// "not written yet" mark of the edge channel: a signalling-NaN bit pattern arithmetic never produces
+#define EX_SENT 0x7FF4DEADBEEF1234ULL
+#define EX_SPIN_LIMIT (4000000000LL)   // cycles (~2 s): a stuck neighbour becomes an error, not a hang
+
+struct SsorParams {
+  int nx, ny, nstrips, zero_old;
+  const double *R, *AC, *AXL, *AYD, *AXR, *AYT;
+  double* Z;
+  unsigned long long* bnd;       // [nstrips][ny]: edge column of strip s, all EX_SENT between sweeps
+  double omega, om1;
+  int* err;
+};
+
+struct SsorEnt { double r, ac, axl, ayd, zo, zs, axr; };
+
+// Operands of cell (j, tt - j): own r, ac, left/lower face, own old z; the right face (the left
+// face of cell (j+1,k), or the boundary face); the old z of the downstream horizontal neighbour.
+template <int DIR>
+__device__ __forceinline__ SsorEnt ssor_load(const SsorParams& P, int tt, int j, bool jvalid)
+{
+  SsorEnt e = {0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  const int k = tt - j;
+  if (jvalid && k >= 0 && k < P.ny) {
+    const long long c = wf_base(tt, P.nx, P.ny) + j;
+    e.r = __ldg(P.R + c);
+    e.ac = __ldg(P.AC + c);
+    e.axl = __ldg(P.AXL + c);
+    e.ayd = __ldg(P.AYD + c);
+    e.axr = (j + 1 < P.nx) ? __ldg(P.AXL + wf_base(tt + 1, P.nx, P.ny) + j + 1) : __ldg(P.AXR + k);
+    if (!P.zero_old) {
+      e.zo = P.Z[c];
+      const int jj = j + DIR;
+      if (jj >= 0 && jj < P.nx) e.zs = P.Z[wf_base(tt + DIR, P.nx, P.ny) + jj];
+    }
+  }
+  return e;
+}
+
+__device__ __noinline__ unsigned long long ssor_wait(volatile unsigned long long* p, int* err)
+{
+  const long long t0 = clock64();
+  unsigned it = 0;
+  for (;;) {
+    const unsigned long long v = *p;
+    if (v != EX_SENT) return v;
+    if ((++it & 63u) == 0u) {
+      if (*(volatile int*)err) return 0ull;
+      if (clock64() - t0 > EX_SPIN_LIMIT) { *(volatile int*)err = 1; return 0ull; }
+    }
+  }
+}
+
+template <int DIR>
+__device__ __forceinline__ void ssor_strip(const SsorParams& P, const int strip, const int lane)
+{
+  constexpr int RING = EX_SSOR_RING, DB = EX_SSOR_DB;
+  const int nx = P.nx, ny = P.ny;
+  const int j = strip * 32 + lane;
+  const bool jvalid = j < nx;
+  const int j0 = strip * 32;
+  const int jlast = j0 + 31 < nx - 1 ? j0 + 31 : nx - 1;
+  const int nsteps = (jlast - j0) + ny;
+  const int t_first = DIR > 0 ? j0 : jlast + ny - 1;
+  const double ayt = jvalid ? __ldg(P.AYT + j) : 0.0;
+  const double omega = P.omega, om1 = P.om1;
+  // forward: lane 31 hands z(j,k) to lane 0 of the next strip; backward: lane 0 to lane 31 of the previous one
+  const bool is_prod = jvalid && (DIR > 0 ? (lane == 31 && j + 1 < nx) : (lane == 0 && strip > 0));
+  const bool is_cons = jvalid && (DIR > 0 ? (lane == 0 && strip > 0) : (lane == 31 && j + 1 < nx));
+  volatile unsigned long long* cout = P.bnd + (size_t)strip * ny;
+  volatile unsigned long long* cin = P.bnd + (size_t)(DIR > 0 ? (strip > 0 ? strip - 1 : 0) : (strip + 1 < P.nstrips ? strip + 1 : strip)) * ny;
+
+  SsorEnt q[RING];
+  unsigned long long zb[RING];
+#pragma unroll
+  for (int i = 0; i < RING; ++i) {
+    q[i] = ssor_load<DIR>(P, t_first + DIR * i, j, jvalid);
+    zb[i] = 0ull;
+  }
+#pragma unroll
+  for (int i = 0; i < DB; ++i) {
+    const int kk = t_first + DIR * i - j;
+    if (is_cons && kk >= 0 && kk < ny) zb[i] = cin[kk];
+  }
+
+  double znew = 0.0;        // own result of the previous step = z(j, k-DIR), new
+  double ayd_prev = 0.0;    // backward: lower face of the previous step's cell = upper face of this one
+  for (int sb = 0; sb < nsteps; sb += RING) {
+#pragma unroll
+    for (int s = 0; s < RING; ++s) {
+      const int t = t_first + DIR * (sb + s);
+      const int k = t - j;
+      const bool act = jvalid && k >= 0 && k < ny;
+      const SsorEnt cur = q[s];
+      const SsorEnt& nxt = q[(s + 1) % RING];
+      // upstream horizontal neighbour, new value: the adjacent lane's previous step
+      __syncwarp();
+      double zh = DIR > 0 ? __shfl_up_sync(0xffffffffu, znew, 1) : __shfl_down_sync(0xffffffffu, znew, 1);
+      if (DIR > 0 ? lane == 0 : lane == 31) zh = 0.0;                    // grid edge: boundary value 0
+      if (is_cons && act) {
+        unsigned long long v = zb[s];
+        if (v == EX_SENT) v = ssor_wait(cin + k, P.err);
+        zh = __longlong_as_double((long long)v);
+        cin[k] = EX_SENT;                                                // ready for the next sweep
+      }
+      const double zvo = nxt.zo;                                         // old z(j, k+DIR); 0 outside the grid
+      const double ayu = (k + 1 < ny) ? (DIR > 0 ? nxt.ayd : ayd_prev) : ayt;
+      const double zl = DIR > 0 ? zh : cur.zs, zr = DIR > 0 ? cur.zs : zh;
+      const double zd = DIR > 0 ? znew : zvo, zu = DIR > 0 ? zvo : znew;
+      // src-F08/nka_example.F90:163-165 (= :171-173), the reference's operation order, no fma
+      double sm = __dadd_rn(cur.r, __dmul_rn(cur.axl, zl));
+      sm = __dadd_rn(sm, __dmul_rn(cur.axr, zr));
+      sm = __dadd_rn(sm, __dmul_rn(cur.ayd, zd));
+      sm = __dadd_rn(sm, __dmul_rn(ayu, zu));
+      const double zc = __dadd_rn(__dmul_rn(om1, cur.zo), __ddiv_rn(__dmul_rn(omega, sm), cur.ac));
+      if (act) {
+        znew = zc;
+        ayd_prev = cur.ayd;
+        P.Z[wf_base(t, nx, ny) + j] = zc;
+        if (is_prod) cout[k] = (unsigned long long)__double_as_longlong(zc);
+      }
+      q[s] = ssor_load<DIR>(P, t + DIR * RING, j, jvalid);
+      {
+        const int kk = t + DIR * DB - j;
+        zb[(s + DB) % RING] = (is_cons && kk >= 0 && kk < ny) ? cin[kk] : 0ull;
+      }
+    }
+  }
+}
+
+template <int DIR>
+__global__ void __launch_bounds__(EX_SSOR_WARPS * 32, 1) ex_ssor_sweep(SsorParams P)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int slots = gridDim.x * EX_SSOR_WARPS;
+  // strips in dependency order: a strip only waits for one that an earlier slot (or an earlier
+  // round of the last slot) owns, and every CTA of the grid is resident, so no wait can deadlock
+  for (int i = blockIdx.x * EX_SSOR_WARPS + warp; i < P.nstrips; i += slots)
+    ssor_strip<DIR>(P, DIR > 0 ? i : P.nstrips - 1 - i, lane);
+}
+
+// ---------------------------------------------------------------------------
+// the handle
+// ---------------------------------------------------------------------------
+struct ExSpan { cudaEvent_t beg, end; int kind; };
+
+struct nka_system {
+  int nx = 0, ny = 0, scaling = 1;
+  double a = 0.0, hx = 0.0, hy = 0.0, fx = 0.0, fy = 0.0, q = 0.0;
+  size_t n = 0;
+  int device = 0, num_sms = 0;
+  cudaStream_t stream = nullptr;
+  double* U[2] = {nullptr, nullptr};
+  int cur = 0;
+  double *R = nullptr, *Z = nullptr, *AXL = nullptr, *AYD = nullptr, *AC = nullptr, *AXR = nullptr, *AYT = nullptr;
+  unsigned long long* bnd = nullptr;
+  int nstrips = 0;
+  double* partials = nullptr;
+  unsigned* ticket = nullptr;
+  double* result = nullptr;        // device: [0] = sum r^2, [1] = error word of the SSOR kernels
+  double* result_host = nullptr;   // pinned
+  double* stage = nullptr;         // device scratch for the order conversions
+  int ssor_grid = 0;
+  bool bnd_dirty = true;
+  int error = 0;
+  unsigned long long launches = 0;
+  bool timing = false;
+  std::vector<ExSpan> spans;
+  double t_ms[2] = {0.0, 0.0};
+  unsigned long long t_cnt[2] = {0, 0};
+};
+
+static void ex_fold(NKASYS sy)
+{
+  if (sy->spans.empty()) return;
+  CUDA_CHECK(cudaStreamSynchronize(sy->stream));
+  for (const ExSpan& sp : sy->spans) {
+    float ms = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&ms, sp.beg, sp.end));
+    sy->t_ms[sp.kind] += ms;
+    sy->t_cnt[sp.kind] += 1;
+    cudaEventDestroy(sp.beg);
+    cudaEventDestroy(sp.end);
+  }
+  sy->spans.clear();
+}
+
+struct ExScope {
+  NKASYS sy; int kind; cudaEvent_t beg = nullptr;
+  ExScope(NKASYS s, int k) : sy(s), kind(k) {
+    if (sy->timing) { CUDA_CHECK(cudaEventCreate(&beg)); CUDA_CHECK(cudaEventRecord(beg, sy->stream)); }
+  }
+  ~ExScope() {
+    if (beg) {
+      cudaEvent_t end;
+      CUDA_CHECK(cudaEventCreate(&end));
+      CUDA_CHECK(cudaEventRecord(end, sy->stream));
+      sy->spans.push_back({beg, end, kind});
+      if (sy->spans.size() >= 4096) ex_fold(sy);
+    }
+  }
+};
+
+extern "C" NKASYS nka_system_init(int nx, int ny, double a, int scaling, int device, void* stream)
+{
+  // preconditions: src-F08/nka_example.F90:90-92
+  NKA_REQUIRE(a > 0.0, "nka_system_init: a must be > 0");
+  NKA_REQUIRE(nx >= 3 && ny >= 3, "nka_system_init: nx, ny must be >= 3");
+  NKA_REQUIRE(nx <= (1 << 20) && ny <= (1 << 20), "nka_system_init: grid too large");
+  NKA_REQUIRE(scaling == 0 || scaling == 1, "nka_system_init: scaling must be 0 (F95/C) or 1 (F08)");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    nka_fail(__FILE__, __LINE__, "no CUDA device: libnka_b200 has no CPU compute path");
+  NKASYS sy = new nka_system();
+  if (device < 0) CUDA_CHECK(cudaGetDevice(&device));
+  sy->device = device;
+  DeviceGuard guard(device);
+  CUDA_CHECK(cudaDeviceGetAttribute(&sy->num_sms, cudaDevAttrMultiProcessorCount, device));
+  sy->stream = (cudaStream_t)stream;
+  sy->nx = nx; sy->ny = ny; sy->a = a; sy->scaling = scaling;
+  sy->n = (size_t)nx * ny;
+  sy->hx = 1.0 / nx; sy->hy = 1.0 / ny;
+  if (scaling == 0) { sy->fx = sy->hx / sy->hy; sy->fy = sy->hy / sy->hx; sy->q = sy->hx * sy->hy; }   // src-C/nka_example.c:97,225-226
+  else { sy->fx = sy->hx * sy->hx; sy->fy = sy->hy * sy->hy; sy->q = 1.0; }                           // F08 :100,:132-135
+  const size_t bytes = sy->n * sizeof(double);
+  double** grids[] = {&sy->U[0], &sy->U[1], &sy->R, &sy->Z, &sy->AXL, &sy->AYD, &sy->AC};
+  for (double** g : grids) {
+    if (cudaMalloc(g, bytes) != cudaSuccess) nka_fail(__FILE__, __LINE__, "nka_system_init: out of device memory");
+    CUDA_CHECK(cudaMemsetAsync(*g, 0, bytes, sy->stream));
+  }
+  CUDA_CHECK(cudaMalloc(&sy->AXR, ny * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&sy->AYT, nx * sizeof(double)));
+  sy->nstrips = (nx + 31) / 32;
+  CUDA_CHECK(cudaMalloc(&sy->bnd, (size_t)sy->nstrips * ny * sizeof(unsigned long long)));
+  const size_t nblk = (size_t)(nx + ny - 1) * (((nx < ny ? nx : ny) + EX_RES_THREADS - 1) / EX_RES_THREADS);
+  CUDA_CHECK(cudaMalloc(&sy->partials, nblk * sizeof(double)));
+  CUDA_CHECK(cudaMalloc(&sy->ticket, sizeof(unsigned)));
+  CUDA_CHECK(cudaMemsetAsync(sy->ticket, 0, sizeof(unsigned), sy->stream));
+  CUDA_CHECK(cudaMalloc(&sy->result, 2 * sizeof(double)));
+  CUDA_CHECK(cudaMemsetAsync(sy->result, 0, 2 * sizeof(double), sy->stream));
+  CUDA_CHECK(cudaMallocHost(&sy->result_host, 2 * sizeof(double)));
+  int occ = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep<1>, EX_SSOR_WARPS * 32, 0));
+  int occb = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep<-1>, EX_SSOR_WARPS * 32, 0));
+  if (occb < occ) occ = occb;
+  NKA_REQUIRE(occ >= 1, "nka_system_init: the SSOR kernel does not fit on an SM");
+  const int want = (sy->nstrips + EX_SSOR_WARPS - 1) / EX_SSOR_WARPS;
+  const int cap = occ * sy->num_sms;
+  sy->ssor_grid = want < cap ? want : cap;
+  return sy;
+}
+
+extern "C" void nka_system_delete(NKASYS sy)
+{
+  if (!sy) return;
+  DeviceGuard guard(sy->device);
+  cudaStreamSynchronize(sy->stream);
+  for (const ExSpan& sp : sy->spans) { cudaEventDestroy(sp.beg); cudaEventDestroy(sp.end); }
+  cudaFree(sy->U[0]); cudaFree(sy->U[1]); cudaFree(sy->R); cudaFree(sy->Z); cudaFree(sy->AXL);
+  cudaFree(sy->AYD); cudaFree(sy->AC); cudaFree(sy->AXR); cudaFree(sy->AYT); cudaFree(sy->bnd);
+  cudaFree(sy->partials); cudaFree(sy->ticket); cudaFree(sy->result); cudaFree(sy->stage);
+  cudaFreeHost(sy->result_host);
+  delete sy;
+}
+
+extern "C" size_t nka_system_size(NKASYS sy) { NKA_REQUIRE(sy != NULL, "nka_system_size: null handle"); return sy->n; }
+extern "C" void* nka_system_stream(NKASYS sy) { NKA_REQUIRE(sy != NULL, "nka_system_stream: null handle"); return (void*)sy->stream; }
+
+extern "C" double* nka_system_field(NKASYS sy, int field)
+{
+  NKA_REQUIRE(sy != NULL, "nka_system_field: null handle");
+  switch (field) {
+    case NKA_FIELD_U: return sy->U[sy->cur];
+    case NKA_FIELD_R: return sy->R;
+    case NKA_FIELD_Z: return sy->Z;
+    case NKA_FIELD_AXL: return sy->AXL;
+    case NKA_FIELD_AYD: return sy->AYD;
+    case NKA_FIELD_AC: return sy->AC;
+  }
+  nka_fail(__FILE__, __LINE__, "nka_system_field: unknown field");
+}
+
+extern "C" size_t nka_system_index(NKASYS sy, int j, int k)
+{
+  NKA_REQUIRE(sy != NULL, "nka_system_index: null handle");
+  NKA_REQUIRE(j >= 0 && j < sy->nx && k >= 0 && k < sy->ny, "nka_system_index: cell out of range");
+  return (size_t)(wf_base(j + k, sy->nx, sy->ny) + j);
+}
+
+static int ex_grid(NKASYS sy, size_t work, int threads)
+{
+  size_t need = (work + threads - 1) / threads, cap = (size_t)sy->num_sms * 16;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+extern "C" void nka_system_set_field(NKASYS sy, int field, const double* host)
+{
+  double* dst = nka_system_field(sy, field);
+  DeviceGuard guard(sy->device);
+  if (!sy->stage) CUDA_CHECK(cudaMalloc(&sy->stage, sy->n * sizeof(double)));
+  CUDA_CHECK(cudaMemcpyAsync(sy->stage, host, sy->n * sizeof(double), cudaMemcpyHostToDevice, sy->stream));
+  ex_permute_kernel<<<ex_grid(sy, sy->n, 256), 256, 0, sy->stream>>>(dst, sy->stage, sy->nx, sy->ny, 1);
+  CUDA_CHECK(cudaGetLastError());
+  sy->launches += 1;
+  CUDA_CHECK(cudaStreamSynchronize(sy->stream));
+}
+
+extern "C" void nka_system_get_field(NKASYS sy, int field, double* host)
+{
+  const double* src = nka_system_field(sy, field);
+  DeviceGuard guard(sy->device);
+  if (!sy->stage) CUDA_CHECK(cudaMalloc(&sy->stage, sy->n * sizeof(double)));
+  ex_permute_kernel<<<ex_grid(sy, sy->n, 256), 256, 0, sy->stream>>>(sy->stage, src, sy->nx, sy->ny, 0);
+  CUDA_CHECK(cudaGetLastError());
+  sy->launches += 1;
+  CUDA_CHECK(cudaMemcpyAsync(host, sy->stage, sy->n * sizeof(double), cudaMemcpyDeviceToHost, sy->stream));
+  CUDA_CHECK(cudaStreamSynchronize(sy->stream));
+}
+
+extern "C" double nka_system_residual(NKASYS sy, int subtract_z)
+{
+  NKA_REQUIRE(sy != NULL, "nka_system_residual: null handle");
+  DeviceGuard guard(sy->device);
+  ResParams P;
+  P.nx = sy->nx; P.ny = sy->ny;
+  P.U = sy->U[sy->cur];
+  P.Zc = subtract_z ? sy->Z : nullptr;
+  P.Unew = sy->U[sy->cur ^ 1];
+  P.R = sy->R; P.AXL = sy->AXL; P.AYD = sy->AYD; P.AC = sy->AC; P.AXR = sy->AXR; P.AYT = sy->AYT;
+  P.a = sy->a; P.fx = sy->fx; P.fy = sy->fy; P.q = sy->q;
+  P.partials = sy->partials; P.ticket = sy->ticket; P.sumsq = sy->result;
+  const int maxlen = sy->nx < sy->ny ? sy->nx : sy->ny;
+  dim3 grid(sy->nx + sy->ny - 1, (maxlen + EX_RES_THREADS - 1) / EX_RES_THREADS);
+  {
+    ExScope t(sy, 1);
+    ex_residual_kernel<<<grid, EX_RES_THREADS, 0, sy->stream>>>(P);
+    CUDA_CHECK(cudaGetLastError());
+    sy->launches += 1;
+  }
+  if (subtract_z) sy->cur ^= 1;
+  CUDA_CHECK(cudaMemcpyAsync(sy->result_host, sy->result, 2 * sizeof(double), cudaMemcpyDeviceToHost, sy->stream));
+  CUDA_CHECK(cudaStreamSynchronize(sy->stream));
+  int errw = 0;
+  memcpy(&errw, &sy->result_host[1], sizeof errw);
+  if (errw) { sy->error = errw; sy->bnd_dirty = true; }
+  return sqrt(sy->result_host[0]);
+}
+
+extern "C" int nka_system_pc_ssor(NKASYS sy, int nsweep, double omega)
+{
+  NKA_REQUIRE(sy != NULL, "nka_system_pc_ssor: null handle");
+  NKA_REQUIRE(nsweep >= 1, "nka_system_pc_ssor: nsweep must be >= 1");       // F08 :156-157
+  NKA_REQUIRE(omega > 0.0, "nka_system_pc_ssor: omega must be > 0");
+  DeviceGuard guard(sy->device);
+  if (sy->bnd_dirty) {
+    const size_t nb = (size_t)sy->nstrips * sy->ny;
+    ex_fill_u64<<<ex_grid(sy, nb, 256), 256, 0, sy->stream>>>(sy->bnd, nb, EX_SENT);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemsetAsync(sy->result + 1, 0, sizeof(double), sy->stream));
+    sy->launches += 1;
+    sy->bnd_dirty = false;
+  }
+  SsorParams P;
+  P.nx = sy->nx; P.ny = sy->ny; P.nstrips = sy->nstrips;
+  P.R = sy->R; P.AC = sy->AC; P.AXL = sy->AXL; P.AYD = sy->AYD; P.AXR = sy->AXR; P.AYT = sy->AYT;
+  P.Z = sy->Z; P.bnd = sy->bnd;
+  P.omega = omega; P.om1 = 1.0 - omega;
+  P.err = reinterpret_cast<int*>(sy->result + 1);
+  ExScope t(sy, 0);
+  for (int i = 0; i < nsweep; ++i) {
+    P.zero_old = (i == 0) ? 1 : 0;                       // z = 0 start (:158): nothing to read yet
+    ex_ssor_sweep<1><<<sy->ssor_grid, EX_SSOR_WARPS * 32, 0, sy->stream>>>(P);
+    CUDA_CHECK(cudaGetLastError());
+    P.zero_old = 0;
+    ex_ssor_sweep<-1><<<sy->ssor_grid, EX_SSOR_WARPS * 32, 0, sy->stream>>>(P);
+    CUDA_CHECK(cudaGetLastError());
+    sy->launches += 2;
+  }
+  return sy->error;
+}
+
+extern "C" int nka_example_solve(NKASYS sy, NKA acc, int nsweep, double omega, int maxitr, double tol,
+                                 double* rnorm, int* nvec_seq)
+{
+  NKA_REQUIRE(sy != NULL && rnorm != NULL, "nka_example_solve: null argument");
+  if (acc) {
+    NKA_REQUIRE(nka_vec_len64(acc) == sy->n, "nka_example_solve: the accelerator's vlen must be nx*ny");
+    NKA_REQUIRE(nka_get_stream(acc) == (void*)sy->stream, "nka_example_solve: accelerator and system must share a stream");
+  }
+  // src-F08/nka_example.F90:242-255 ; src-C/nka_example.c:131-166
+  const double rnorm0 = nka_system_residual(sy, 0);
+  rnorm[0] = rnorm0;
+  int itr;
+  for (itr = 1; itr <= maxitr; ++itr) {
+    nka_system_pc_ssor(sy, nsweep, omega);
+    if (acc) {
+      nka_accel_update_dev(acc, sy->Z);
+      if (nvec_seq) nvec_seq[itr - 1] = nka_num_vec(acc);
+    }
+    rnorm[itr] = nka_system_residual(sy, 1);
+    if (sy->error) nka_fail(__FILE__, __LINE__, "nka_example_solve: an SSOR sweep timed out waiting for its neighbour strip");
+    if (rnorm[itr] < tol * rnorm0) break;
+  }
+  return itr > maxitr ? maxitr : itr;
+}
+
+extern "C" void nka_system_timing_enable(NKASYS sy, int on)
+{
+  NKA_REQUIRE(sy != NULL, "nka_system_timing_enable: null handle");
+  DeviceGuard guard(sy->device);
+  if (!on) ex_fold(sy);
+  else { sy->t_ms[0] = sy->t_ms[1] = 0.0; sy->t_cnt[0] = sy->t_cnt[1] = 0; }
+  sy->timing = on != 0;
+}
+
+extern "C" void nka_system_timing_read(NKASYS sy, double ms[2], unsigned long long count[2])
+{
+  NKA_REQUIRE(sy != NULL, "nka_system_timing_read: null handle");
+  DeviceGuard guard(sy->device);
+  ex_fold(sy);
+  for (int k = 0; k < 2; ++k) { ms[k] = sy->t_ms[k]; count[k] = sy->t_cnt[k]; }
+}
+
+extern "C" unsigned long long nka_system_launch_count(NKASYS sy)
+{
+  NKA_REQUIRE(sy != NULL, "nka_system_launch_count: null handle");
+  return sy->launches;
+}

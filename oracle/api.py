@@ -209,6 +209,59 @@ class RefNKA:
             pass
 
 
+
+class _OrcSystemStruct(C.Structure):
+    """oracle/nka_oracle.c: struct orc_system"""
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("scaling", C.c_int),
+                ("a", C.c_double), ("hx", C.c_double), ("hy", C.c_double),
+                ("ax", _dbl_p), ("ay", _dbl_p), ("ac", _dbl_p), ("q", _dbl_p)]
+
+
+class OracleSystem:
+    """The restated example system (system_type: src-F08/nka_example.F90:67-181), one call at a
+    time, natural order: r[k*nx + j]; u is padded (ny+2, nx+2) with the boundary values."""
+
+    def __init__(self, nx: int, ny: int, a: float = 0.02, scaling: int = 1):
+        self._lib = oracle_lib()
+        self.nx, self.ny = nx, ny
+        self._h = self._lib.orc_system_init(nx, ny, a, scaling)
+
+    def residual(self, upad: np.ndarray) -> np.ndarray:
+        r = np.zeros(self.nx * self.ny)
+        self._lib.orc_residual(self._h, _dp(np.ascontiguousarray(upad, dtype=np.float64).ravel()), _dp(r))
+        return r
+
+    def pc_ssor(self, nsweep: int, omega: float, r: np.ndarray) -> np.ndarray:
+        z = np.array(r, dtype=np.float64).ravel().copy()
+        self._lib.orc_ssor(self._h, nsweep, omega, _dp(z))
+        return z
+
+    def coefficients(self):
+        """(ax[(ny, nx+1)], ay[(ny+1, nx)], ac[(ny, nx)]) of the last residual call."""
+        st = C.cast(self._h, C.POINTER(_OrcSystemStruct)).contents
+        nx, ny = self.nx, self.ny
+        ax = np.ctypeslib.as_array(st.ax, shape=(ny * (nx + 1),)).reshape(ny, nx + 1).copy()
+        ay = np.ctypeslib.as_array(st.ay, shape=((ny + 1) * nx,)).reshape(ny + 1, nx).copy()
+        ac = np.ctypeslib.as_array(st.ac, shape=(ny * nx,)).reshape(ny, nx).copy()
+        return ax, ay, ac
+
+    @staticmethod
+    def norm2(x: np.ndarray) -> float:
+        x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+        return oracle_lib().orc_l2norm(_dp(x), x.size)
+
+    def close(self):
+        if self._h:
+            self._lib.orc_system_delete(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def example_solve(nx=50, ny=50, a=0.02, nsweep=2, omega=1.4, mvec=5, vtol=0.01, scaling=0,
                   flavour=0, maxitr=999, tol=1.0e-6, record=False):
     """Run the restated example; returns dict(iters, rnorm[, fseq, gseq, nvec], u)."""
