@@ -26,8 +26,10 @@ def test_vector_ops_match_grid_vector_expressions(n):
     np.testing.assert_allclose(z.get(), hz, rtol=0, atol=1e-15)
     z.update(a, x, b, y, c); hz = a * hx + b * hy + c * hz  # update4_ :157-168
     np.testing.assert_allclose(z.get(), hz, rtol=0, atol=1e-15)
+    before = z.get()                                      # (host hz now differs from z by fma roundings)
     z.scale(-2.0); hz = -2.0 * hz                         # scale     :114-118
-    assert np.array_equal(z.get(), hz)
+    assert np.array_equal(z.get(), -2.0 * before)
+    np.testing.assert_allclose(z.get(), hz, rtol=0, atol=4e-15)
     # zero-coefficient short cuts of the base class (vector_class.F90:176,189,203-206)
     before = z.get()
     z.update(0.0, x); assert np.array_equal(z.get(), before)

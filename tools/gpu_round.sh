@@ -39,6 +39,17 @@ try:
 except Exception as e: print("parse failed", e)
 PY
   done ;;
+sweep)
+  : > gpurun_out/mvec_sweep_$tag.jsonl
+  for m in 2 5 10 20; do
+    TUNE_M=$m TUNE_TAG="mvec$m" timeout 300 python tools/tune.py >> gpurun_out/mvec_sweep_$tag.jsonl 2>> gpurun_out/mvec_sweep_$tag.err
+  done
+  cat gpurun_out/mvec_sweep_$tag.jsonl | cut -c1-600 ;;
+example)
+  for N in 4096; do
+    timeout 600 python tools/example_time.py $N 20 5 >> gpurun_out/example_$tag.jsonl 2>> gpurun_out/example_$tag.err
+  done
+  cat gpurun_out/example_$tag.jsonl ;;
 tune)
   : > gpurun_out/tune_$tag.jsonl
   for lib in ${TUNE_LIBS:-default t256_b2 t512_b1 t256_b1_st0 t512_b1_st0 t512_b1_ld0 t1024_b1}; do

@@ -13,6 +13,17 @@ import torch  # noqa: E402
 from nka_b200 import NKA  # noqa: E402
 
 
+def _peak():
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        return float(json.load(open(os.path.join(root, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6554.9
+
+
+PEAK = _peak()
+
+
 def main():
     n = int(os.environ.get("TUNE_N", str(1 << 28)))
     m = int(os.environ.get("TUNE_M", "10"))
@@ -43,7 +54,8 @@ def main():
         "ms_state": t["state"]["ms"] / steps, "ms_mat": t["materialise"]["ms"] / max(t["materialise"]["count"], 1),
         "lazy": lazy,
         "tbs_a_actual": (m + (1 if lazy else 2)) * n * 8 / a / 1e9, "tbs_b_actual": (m + 4) * n * 8 / b / 1e9,
-        "updates_per_s": 1e3 / total, "frac_roofline": (2 * m + 4) * n * 8 / (total * 1e-3) / 1e9 / 6554.9,
+        "updates_per_s": 1e3 / total, "frac_roofline": (2 * m + 4) * n * 8 / (total * 1e-3) / 1e9 / PEAK,
+        "hbm_gbs": (2 * m + 4) * n * 8 / (total * 1e-3) / 1e9, "peak_gbs": PEAK,
         "num_vec": acc.num_vec(),
     }
     print(json.dumps(out))
