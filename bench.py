@@ -184,7 +184,7 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(args, n_local):
+def workload_config(args, n_local, comm_mode=None):
     cfg = {
         "workload": "synthetic accel_update microbench (BASELINE.json configs[2]): n=2^%d fp64, mvec=%d, vtol=%g, "
                     "steady state (subspace full, one eviction per call), f_t i.i.d. uniform(-0.5,0.5)"
@@ -192,7 +192,10 @@ def workload_config(args, n_local):
         "n": args.n, "mvec": args.mvec, "vtol": VTOL,
         "l2": "inputs larger than L2: every column is %.0f MiB per GPU, no flush needed"
               % ((n_local or args.n) * 8 / 2 ** 20),
-        "parallelism": "row slabs, %d GPU(s), one 66-double NCCL all-reduce per update" % args.gpus
+        "parallelism": ("row slabs, %d GPU(s), %s" % (args.gpus, {
+            "peer": "partial dot products summed across ranks inside pass A through NVLink peer memory "
+                    "(no collective launch)",
+            "nccl": "one 66-double NCCL all-reduce per update"}.get(comm_mode, "one small sum-allreduce per update")))
                        if args.gpus > 1 else "single GPU",
     }
     if n_local is not None:
@@ -348,7 +351,8 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, n_local),
+            "config": workload_config(args, n_local, acc.comm_mode()),
+            "comm_mode": acc.comm_mode(),
             "hbm_gbs": gbs, "roofline_frac_update": gbs / (peak * world),
             "roofline_update": {"algorithmic_bytes": algo, "formula": "(2M+4)*n*8", "achieved_gbs": gbs,
                                 "peak_gbs": peak * world, "frac": gbs / (peak * world),

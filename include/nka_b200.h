@@ -67,6 +67,12 @@ int nka_comm_unique_id (void *id128);
 int nka_comm_init (NKA, int nranks, int rank, const void *id128);
 /* Alternatively adopt an existing ncclComm_t (not owned). */
 void nka_comm_adopt (NKA, void *nccl_comm, int nranks, int rank);
+/* How the partial dot products are summed: 0 = single GPU (no exchange); 1 = one NCCL
+ * all-reduce between pass A and the state kernel; 2 = fused into pass A through peer memory
+ * (every rank maps every peer's exchange box with CUDA IPC; chosen automatically by
+ * nka_comm_init / nka_comm_adopt when all ranks share one NVLink domain, unanimous across
+ * ranks; NKA_PEER_REDUCE=0 in the environment of every rank forces 1). */
+int nka_comm_mode (NKA);
 
 /* ---- device vectors: the operations of the reference's abstract `vector` ---- */
 /* What a concrete gpu_vector extension of src-F08-vector/vector_class.F90:90-109

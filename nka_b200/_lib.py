@@ -51,6 +51,7 @@ SYMBOLS = {
     "nka_comm_unique_id": (C.c_int, [C.c_void_p]),
     "nka_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "nka_comm_adopt": (None, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "nka_comm_mode": (C.c_int, [C.c_void_p]),
     "nka_vec_create": (C.c_void_p, [C.c_size_t, C.c_int, C.c_void_p]),
     "nka_vec_clone": (C.c_void_p, [C.c_void_p]),
     "nka_vec_destroy": (None, [C.c_void_p]),

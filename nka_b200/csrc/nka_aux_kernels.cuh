@@ -22,9 +22,9 @@ __global__ void __launch_bounds__(NKA_STATE_THREADS) nka_state_kernel(NkaDevStat
 __global__ void __launch_bounds__(NKA_THREADS)
 nka_fixup_kernel(const double* __restrict__ f, const double* __restrict__ W, size_t ld, size_t n,
                  NkaDevState* __restrict__ S, double* __restrict__ partials, unsigned* __restrict__ ticket,
-                 double* __restrict__ dots)
+                 double* __restrict__ dots, NkaPeerCtx* __restrict__ peer)
 {
-  if (!S->need_fixup) return;
+  if (!S->need_fixup) return;          // identical on every rank: they ran the state step on the same bits
   const NkaPlanA& A = S->planA;
   const int jl = A.ncol - 1;
   const double* w0 = W + (size_t)A.col[0] * ld;
@@ -41,11 +41,13 @@ nka_fixup_kernel(const double* __restrict__ f, const double* __restrict__ W, siz
     acc[1] = fma(x0, dl, acc[1]);
   }
   __shared__ NkaStateStage sm;
-  const bool last = nka_grid_reduce<2, NKA_THREADS>(acc, partials, ticket, [&](int j, double v) {
-    dots[(j == 0 ? 0 : NKA_MAXSLOT) + jl] = v;
-  });
+  __shared__ double xv[2];
+  const bool last = nka_grid_reduce<2, NKA_THREADS>(acc, partials, ticket, [&](int j, double v) { xv[j] = v; });
   if (last) {
+    if (peer) nka_peer_allreduce(peer, xv, 2);
+    if (threadIdx.x < 2) dots[(threadIdx.x == 0 ? 0 : NKA_MAXSLOT) + jl] = xv[threadIdx.x];
     __threadfence();
+    __syncthreads();
     nka_stage_in(sm, S, dots);
     nka_run_state_step(sm, S, /*have_last=*/1);
   }

@@ -64,6 +64,7 @@ bool nka_nccl_load()
   g_nccl.GetUniqueId = (int (*)(void*))dlsym(g_nccl.lib, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(void**, int, NkaId128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
   return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
@@ -108,6 +109,11 @@ struct nka_state {
   bool lazy = true;             // skip the doomed oldest column in pass A (single GPU only)
   // distributed
   NkaComm* comm = nullptr;
+  // peer-memory reduction fused into pass A (all ranks on one NVLink domain); else NCCL
+  NkaPeerCtx* peer = nullptr;   // device copy of the context; nullptr = not in use
+  void* peer_box = nullptr;     // this rank's exchange box (device memory, IPC-exported)
+  void* peer_mapped[NKA_MAX_RANKS] = {};   // the peers' boxes as opened here
+  int peer_n = 0;
   // accounting
   unsigned long long launches = 0;
   bool timing = false;
@@ -200,6 +206,91 @@ static int nz_expected(NKA st)
 }
 
 // ---------------------------------------------------------------------------
+// peer-memory exchange boxes (multi-GPU, one process per GPU, one NVLink domain)
+// ---------------------------------------------------------------------------
+static const size_t kPeerBoxBytes = 2u << 20;    // a whole 2 MiB allocation of its own: what CUDA IPC exports
+
+static void peer_teardown(NKA st)
+{
+  if (!st->peer && !st->peer_box) return;
+  DeviceGuard guard(st->device);
+  cudaStreamSynchronize(st->stream);
+  for (int r = 0; r < st->peer_n; ++r)
+    if (st->peer_mapped[r]) { cudaIpcCloseMemHandle(st->peer_mapped[r]); st->peer_mapped[r] = nullptr; }
+  cudaFree(st->peer); st->peer = nullptr;
+  cudaFree(st->peer_box); st->peer_box = nullptr;
+  st->peer_n = 0;
+  cudaGetLastError();
+}
+
+// Collective over the communicator.  Every rank allocates a box, the IPC handles are
+// all-gathered with NCCL, every rank opens every peer's box, and an all-reduce(min) makes the
+// outcome unanimous: either every rank reduces through peer memory or every rank stays on NCCL.
+static bool peer_setup(NKA st)
+{
+  static_assert(sizeof(uint4) * NKA_PEER_BOX_WORDS16 <= kPeerBoxBytes, "exchange box does not fit its allocation");
+  NkaComm* c = st->comm;
+  if (!c || !g_nccl.AllGather) return false;
+  if (const char* e = getenv("NKA_PEER_REDUCE")) if (atoi(e) == 0) return false;    // ablation: NCCL all-reduce
+  if (c->nranks < 2 || c->nranks > NKA_MAX_RANKS) return false;
+  const int R = c->nranks, me = c->rank;
+  struct Card { cudaIpcMemHandle_t h; int ok; int pad; };
+  Card mine;
+  memset(&mine, 0, sizeof mine);
+  mine.ok = 1;
+  if (cudaMalloc(&st->peer_box, kPeerBoxBytes) != cudaSuccess) { cudaGetLastError(); st->peer_box = nullptr; mine.ok = 0; }
+  if (mine.ok) {
+    CUDA_CHECK(cudaMemsetAsync(st->peer_box, 0, kPeerBoxBytes, st->stream));
+    CUDA_CHECK(cudaStreamSynchronize(st->stream));
+    if (cudaIpcGetMemHandle(&mine.h, st->peer_box) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  }
+  Card* d_cards = nullptr;
+  int* d_flag = nullptr;
+  CUDA_CHECK(cudaMalloc(&d_cards, sizeof(Card) * (R + 1)));
+  CUDA_CHECK(cudaMalloc(&d_flag, sizeof(int)));
+  CUDA_CHECK(cudaMemcpyAsync(d_cards + R, &mine, sizeof mine, cudaMemcpyHostToDevice, st->stream));
+  int rc = g_nccl.AllGather(d_cards + R, d_cards, sizeof(Card), kNcclChar, c->comm, st->stream);
+  if (rc != 0) nka_fail(__FILE__, __LINE__, "ncclAllGather (peer box handles) failed");
+  std::vector<Card> cards(R);
+  CUDA_CHECK(cudaMemcpyAsync(cards.data(), d_cards, sizeof(Card) * R, cudaMemcpyDeviceToHost, st->stream));
+  CUDA_CHECK(cudaStreamSynchronize(st->stream));
+  int ok = 1;
+  for (int r = 0; r < R; ++r) ok &= cards[r].ok;
+  NkaPeerCtx ctx;
+  memset(&ctx, 0, sizeof ctx);
+  ctx.nranks = R; ctx.rank = me; ctx.epoch = 0; ctx.timed_out = 0;
+  double timeout_s = 120.0;                       // NKA_PEER_TIMEOUT_S: how long to wait for a peer before trapping
+  if (const char* e = getenv("NKA_PEER_TIMEOUT_S")) if (atof(e) > 0.0) timeout_s = atof(e);
+  ctx.timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  st->peer_n = R;
+  if (ok) {
+    for (int r = 0; r < R; ++r) {
+      if (r == me) { ctx.box[r] = st->peer_box; continue; }
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, cards[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        break;
+      }
+      st->peer_mapped[r] = p;
+      ctx.box[r] = p;
+    }
+  }
+  CUDA_CHECK(cudaMemcpyAsync(d_flag, &ok, sizeof ok, cudaMemcpyHostToDevice, st->stream));
+  rc = g_nccl.AllReduce(d_flag, d_flag, 1, kNcclInt32, kNcclMin, c->comm, st->stream);
+  if (rc != 0) nka_fail(__FILE__, __LINE__, "ncclAllReduce (peer box agreement) failed");
+  CUDA_CHECK(cudaMemcpyAsync(&ok, d_flag, sizeof ok, cudaMemcpyDeviceToHost, st->stream));
+  CUDA_CHECK(cudaStreamSynchronize(st->stream));
+  cudaFree(d_cards);
+  cudaFree(d_flag);
+  if (!ok) { peer_teardown(st); return false; }
+  CUDA_CHECK(cudaMalloc(&st->peer, sizeof(NkaPeerCtx)));
+  CUDA_CHECK(cudaMemcpyAsync(st->peer, &ctx, sizeof ctx, cudaMemcpyHostToDevice, st->stream));
+  CUDA_CHECK(cudaStreamSynchronize(st->stream));
+  return true;
+}
+
+// ---------------------------------------------------------------------------
 // construction / destruction
 // ---------------------------------------------------------------------------
 extern "C" NKA nka_init_ex(size_t vlen, int mvec, double vtol, int device, void* stream)
@@ -281,6 +372,7 @@ extern "C" void nka_delete(NKA st)
   cudaStreamSynchronize(st->stream);
   for (const TimedSpan& sp : st->spans) { cudaEventDestroy(sp.beg); cudaEventDestroy(sp.end); }
   for (cudaEvent_t ev : st->free_events) cudaEventDestroy(ev);
+  peer_teardown(st);
   nka_comm_release(st->comm);
   cudaFree(st->W); cudaFree(st->Z); cudaFree(st->S); cudaFree(st->dots);
   cudaFree(st->partials); cudaFree(st->ticket); cudaFree(st->fstage);
@@ -299,7 +391,9 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
   const size_t n = st->vlen;
   const int V = (((uintptr_t)f) % 16 == 0) ? 2 : 1;
   const int L = st->ub_len;                         // upper bound on the list length at entry
-  const bool single = (st->comm == nullptr);        // single GPU: fused state step, lazy last column
+  // fused = the dot products are complete when pass A's last CTA has them (single GPU, or
+  // summed over the ranks through peer memory inside pass A): state step in place, lazy last column
+  const bool single = (st->comm == nullptr) || (st->peer != nullptr);
   const bool may_skip = single && st->lazy && st->pending && L == st->mvec + 1;
   const int NC = may_skip ? st->mvec : L;           // columns pass A can be asked to stream
 
@@ -308,7 +402,7 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
     {
       SpanScope t(st, T_PASS_A);
       nka_get_pass_a(NC, V)<<<grid, NKA_THREADS_A, 0, st->stream>>>(f, st->W, st->ld, n, st->S, st->partials, st->ticket,
-                                                            st->dots, single ? 1 : 0);
+                                                            st->dots, single ? 1 : 0, st->peer);
       CUDA_CHECK(cudaGetLastError());
       st->launches += 1;
     }
@@ -327,7 +421,7 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
       // (or the s == 0 guard) means it is needed after all
       SpanScope t(st, T_STATE);
       nka_fixup_kernel<<<grid_for(st, 4, n, 1), NKA_THREADS, 0, st->stream>>>(f, st->W, st->ld, n, st->S, st->partials,
-                                                                             st->ticket, st->dots);
+                                                                             st->ticket, st->dots, st->peer);
       CUDA_CHECK(cudaGetLastError());
       st->launches += 1;
     }
@@ -515,7 +609,7 @@ extern "C" void nka_launch_geometry(NKA st, int* grid_a, int* grid_b, int* threa
   NKA_REQUIRE(st != NULL, "nka_launch_geometry: null handle");
   DeviceGuard guard(st->device);
   const int L = st->ub_len;
-  const bool may_skip = st->comm == nullptr && st->lazy && st->pending && L == st->mvec + 1;
+  const bool may_skip = (st->comm == nullptr || st->peer != nullptr) && st->lazy && st->pending && L == st->mvec + 1;
   const int NC = may_skip ? st->mvec : L;
   if (grid_a) *grid_a = L > 0 ? grid_for(st, occupancy_a(st, NC, 2), st->vlen, 2, NKA_THREADS_A) : 0;
   const int nz = nz_expected(st);
@@ -536,9 +630,19 @@ extern "C" int nka_comm_unique_id(void* id128)
 
 static void attach_comm(NKA st, NkaComm* c)
 {
+  peer_teardown(st);
   nka_comm_release(st->comm);
   st->comm = c;
-  set_lazy(st, false);     // a conditional second all-reduce is not worth it: every rank streams all columns
+  // On one NVLink domain the reduction is fused into pass A (peer memory).  Otherwise NCCL
+  // reduces between pass A and the state kernel, and the lazy column is off: its conditional
+  // second all-reduce is not worth it, every rank streams all columns.
+  if (!peer_setup(st)) set_lazy(st, false);
+}
+
+extern "C" int nka_comm_mode(NKA st)
+{
+  NKA_REQUIRE(st != NULL, "nka_comm_mode: null handle");
+  return st->comm == nullptr ? 0 : (st->peer ? 2 : 1);
 }
 
 extern "C" int nka_comm_init(NKA st, int nranks, int rank, const void* id128)

@@ -28,6 +28,7 @@ struct NkaNcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, NkaId128, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -35,6 +36,9 @@ extern NkaNcclApi g_nccl;
 bool nka_nccl_load();
 static const int kNcclFloat64 = 8;   // ncclDouble
 static const int kNcclSum = 0;       // ncclSum
+static const int kNcclMin = 3;       // ncclMin
+static const int kNcclChar = 0;      // ncclInt8
+static const int kNcclInt32 = 2;     // ncclInt32
 
 // A reference-counted communicator shared by vectors cloned from one another and by the
 // accelerator created from them.

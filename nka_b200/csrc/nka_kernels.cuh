@@ -182,6 +182,70 @@ __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* 
 }
 
 // ---------------------------------------------------------------------------
+// Cross-GPU sum of K doubles held in shared memory, executed by one CTA per rank
+// (the last CTA of pass A / of the fix-up sweep), fused into that kernel: every
+// rank stores its values straight into every peer's exchange box over NVLink and
+// then folds the R contributions it received in rank order, so all ranks hold
+// bit-identical sums and take identical drop decisions.  One NVLink store
+// latency end to end; no fence, no separate collective launch.
+//   slot = {lo32(v), tag, hi32(v), tag}: each 8-byte half carries the tag, the
+//   receiver spins until both halves show this exchange's tag.
+//   Two parities: a rank can run at most one exchange ahead of a peer (it needs
+//   that peer's contribution to finish the current one), so the slot written
+//   for exchange e+2 has been consumed by everyone.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long nka_globaltimer()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void nka_peer_allreduce(NkaPeerCtx* __restrict__ P, double* vals, int K)
+{
+  __shared__ unsigned ep_s;
+  if (threadIdx.x == 0) ep_s = *reinterpret_cast<volatile unsigned*>(&P->epoch) + 1u;
+  __syncthreads();
+  const unsigned ep = ep_s;
+  const int R = P->nranks, me = P->rank;
+  const unsigned long long timeout_ns = P->timeout_ns;
+  const size_t par = (size_t)(ep & 1u) * NKA_MAX_RANKS * NKA_PEER_K;
+  for (int i = threadIdx.x; i < R * K; i += blockDim.x) {
+    const int r = i / K, t = i - r * K;
+    const double v = vals[t];
+    uint4* dst = reinterpret_cast<uint4*>(P->box[r]) + par + (size_t)me * NKA_PEER_K + t;
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(dst), "r"((unsigned)__double2loint(v)), "r"(ep), "r"((unsigned)__double2hiint(v)), "r"(ep)
+                 : "memory");
+  }
+  __syncthreads();                                   // every value has been read before it is replaced
+  const uint4* mine = reinterpret_cast<const uint4*>(P->box[me]) + par;
+  for (int t = threadIdx.x; t < K; t += blockDim.x) {
+    double sum = 0.0;
+    for (int r = 0; r < R; ++r) {
+      const uint4* src = mine + (size_t)r * NKA_PEER_K + t;
+      unsigned lo, t0, hi, t1;
+      unsigned long long t_start = 0;
+      for (unsigned spins = 0;; ++spins) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                     : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(src) : "memory");
+        if (t0 == ep && t1 == ep) break;
+        if ((spins & 0xfffu) == 0xfffu) {
+          const unsigned long long now = nka_globaltimer();
+          if (t_start == 0) t_start = now;
+          else if (now - t_start > timeout_ns) { P->timed_out = 1; __threadfence_system(); __trap(); }
+        }
+      }
+      const double v = __hiloint2double((int)hi, (int)lo);
+      sum = (r == 0) ? v : sum + v;
+    }
+    vals[t] = sum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned*>(&P->epoch) = ep;
+}
+
+// ---------------------------------------------------------------------------
 // State staging.  The ~11 KB state is worked on in shared memory: the scalar
 // algorithm is a chain of dependent loads, and from global memory every one of
 // them paid an L2 round trip (43 us at mvec = 10 on B200; profiles/r1a_*).
@@ -265,7 +329,7 @@ template <int NC, int V>
 __global__ void __launch_bounds__(NKA_THREADS_A, NKA_MINB_A)
 nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld, size_t n,
            NkaDevState* __restrict__ S, double* __restrict__ partials, unsigned* __restrict__ ticket,
-           double* __restrict__ dots, int fuse_state)
+           double* __restrict__ dots, int fuse_state, NkaPeerCtx* __restrict__ peer)
 {
   const int ncol = S->planA.ncol - S->planA.skip_last;      // columns actually streamed
   const unsigned submask = S->planA.submask;
@@ -290,13 +354,19 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
   if (V == 2 && (n & 1) && start == 0) nka_pass_a_elem<NC, 1, false>(f, wcol, n - 1, ncol, submask, acc);
 
   __shared__ NkaStateStage sm;     // used by the last CTA only
-  const bool last = nka_grid_reduce<2 * NC, NKA_THREADS_A>(acc, partials, ticket, [&](int j, double v) {
+  __shared__ double xv[2 * NC];
+  const bool last = nka_grid_reduce<2 * NC, NKA_THREADS_A>(acc, partials, ticket, [&](int j, double v) { xv[j] = v; });
+  if (!last) return;
+  // multi-GPU on one NVLink domain: sum over the ranks right here, through peer memory
+  if (peer) nka_peer_allreduce(peer, xv, 2 * NC);
+  for (int j = threadIdx.x; j < 2 * NC; j += NKA_THREADS_A) {
     const int at = (j < NC) ? j : (NKA_MAXSLOT + (j - NC));
-    dots[at] = v;
-    sm.dots[at] = v;
-  });
-  if (last && fuse_state) {
-    // single GPU: the scalar step runs right here, no extra launch
+    dots[at] = xv[j];
+    sm.dots[at] = xv[j];
+  }
+  __syncthreads();
+  if (fuse_state) {
+    // the scalar step runs right here, no extra launch
     const uint32_t* src = reinterpret_cast<const uint32_t*>(S);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.st);
     for (unsigned i = threadIdx.x; i < sizeof(NkaDevState) / 4; i += blockDim.x) dst[i] = __ldcg(src + i);

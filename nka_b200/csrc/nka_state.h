@@ -107,6 +107,22 @@ struct NkaDevState {
 
 #define NKA_H(S, r, c_) ((S).h[(r) * NKA_MAXSLOT + (c_)])
 
+// Multi-GPU, one process per GPU on one NVLink domain: the partial dot products are summed
+// across ranks INSIDE pass A (nka_peer_allreduce, nka_kernels.cuh) through exchange boxes that
+// every rank maps into every peer (CUDA IPC).  A box holds, for two alternating parities and
+// each sending rank, NKA_PEER_K 16-byte slots {lo32, tag, hi32, tag}: value and tag travel in
+// one 16-byte store whose two 8-byte halves carry their own tag, so no fence is needed.
+#define NKA_MAX_RANKS 16
+#define NKA_PEER_K (2 * NKA_MAXSLOT)
+#define NKA_PEER_BOX_WORDS16 (2 * NKA_MAX_RANKS * NKA_PEER_K)      // 16-byte slots per box
+struct NkaPeerCtx {
+  void* box[NKA_MAX_RANKS];    // box[r]: rank r's exchange box as mapped in this process
+  int nranks, rank;
+  unsigned epoch;              // exchanges completed (identical on every rank)
+  int timed_out;
+  unsigned long long timeout_ns;   // a peer that never arrives: trap instead of hanging the GPU
+};
+
 NKA_HD void nka_build_plan_a(NkaDevState& S)
 {
   NkaPlanA& A = S.planA;

@@ -118,6 +118,10 @@ class NKA:
         if rc != 0:
             raise NKAError("nka_comm_init failed with NCCL code %d" % rc)
 
+    def comm_mode(self) -> str:
+        """How the partial dot products are summed across ranks (include/nka_b200.h: nka_comm_mode)."""
+        return ("single", "nccl", "peer")[self._lib.nka_comm_mode(self._handle())]
+
     def state(self) -> dict:
         v = _lib.StateView()
         self._lib.nka_get_state(self._handle(), C.byref(v))
