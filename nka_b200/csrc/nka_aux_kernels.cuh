@@ -42,7 +42,8 @@ nka_fixup_kernel(const double* __restrict__ f, const double* __restrict__ W, siz
   }
   __shared__ NkaStateStage sm;
   __shared__ double xv[2];
-  const bool last = nka_grid_reduce<2, NKA_THREADS>(acc, partials, ticket, [&](int j, double v) { xv[j] = v; });
+  const bool last = nka_grid_reduce<2, NKA_THREADS>(acc, partials, ticket, partials, gridDim.x,
+                                                  [&](int j, double v) { xv[j] = v; });
   if (last) {
     if (peer) nka_peer_allreduce(peer, xv, 2);
     if (threadIdx.x < 2) dots[(threadIdx.x == 0 ? 0 : NKA_MAXSLOT) + jl] = xv[threadIdx.x];

@@ -102,6 +102,10 @@ struct nka_state {
   double* partials = nullptr;   // device, max_grid * 2*NKA_MAXSLOT
   unsigned* ticket = nullptr;   // device
   double* fstage = nullptr;     // device staging for host callers, vlen doubles (lazy)
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;   // host callers: PCIe copies overlapped with the sweeps (lazy)
+  cudaEvent_t chunk_ev[16] = {};
+  cudaEvent_t order_ev = nullptr;
+  size_t host_chunk_bytes = 0;
   int max_grid = 0;
   // host-side knowledge of the device list: exact `pending`, upper bound on its length
   bool pending = false;
@@ -376,6 +380,11 @@ extern "C" void nka_delete(NKA st)
   nka_comm_release(st->comm);
   cudaFree(st->W); cudaFree(st->Z); cudaFree(st->S); cudaFree(st->dots);
   cudaFree(st->partials); cudaFree(st->ticket); cudaFree(st->fstage);
+  if (st->copy_in) {
+    cudaStreamDestroy(st->copy_in); cudaStreamDestroy(st->copy_out);
+    for (cudaEvent_t ev : st->chunk_ev) cudaEventDestroy(ev);
+    cudaEventDestroy(st->order_ev);
+  }
   if (st->own_stream) cudaStreamDestroy(st->stream);
   delete st;
 }
@@ -383,30 +392,52 @@ extern "C" void nka_delete(NKA st)
 // ---------------------------------------------------------------------------
 // the hot path
 // ---------------------------------------------------------------------------
-extern "C" void nka_accel_update_dev(NKA st, double* f)
+// One update = pass A (+ exchange + state step), [fix-up], pass B.  Both sweeps are element-wise,
+// so either may be cut into chunks [off, off+len) of the vector launched one after the other on
+// the handle's stream: the host-pointer path does that to overlap them with the PCIe copies.
+struct UpdateShape {
+  int V, L, NC, nz;
+  bool fused, may_skip;
+};
+
+static UpdateShape update_shape(NKA st, const double* f)
 {
-  NKA_REQUIRE(st != NULL, "nka_accel_update: null handle");
-  NKA_REQUIRE(f != NULL || st->vlen == 0, "nka_accel_update: null vector");
-  DeviceGuard guard(st->device);
-  const size_t n = st->vlen;
-  const int V = (((uintptr_t)f) % 16 == 0) ? 2 : 1;
-  const int L = st->ub_len;                         // upper bound on the list length at entry
+  UpdateShape u;
+  u.V = (((uintptr_t)f) % 16 == 0) ? 2 : 1;
+  u.L = st->ub_len;                               // upper bound on the list length at entry
   // fused = the dot products are complete when pass A's last CTA has them (single GPU, or
   // summed over the ranks through peer memory inside pass A): state step in place, lazy last column
-  const bool single = (st->comm == nullptr) || (st->peer != nullptr);
-  const bool may_skip = single && st->lazy && st->pending && L == st->mvec + 1;
-  const int NC = may_skip ? st->mvec : L;           // columns pass A can be asked to stream
+  u.fused = (st->comm == nullptr) || (st->peer != nullptr);
+  u.may_skip = u.fused && st->lazy && st->pending && u.L == st->mvec + 1;
+  u.NC = u.may_skip ? st->mvec : u.L;             // columns pass A can be asked to stream
+  u.nz = nz_expected(st);
+  return u;
+}
 
-  if (L > 0) {
-    const int grid = grid_for(st, occupancy_a(st, NC, V), n, V, NKA_THREADS_A);
-    {
-      SpanScope t(st, T_PASS_A);
-      nka_get_pass_a(NC, V)<<<grid, NKA_THREADS_A, 0, st->stream>>>(f, st->W, st->ld, n, st->S, st->partials, st->ticket,
-                                                            st->dots, single ? 1 : 0, st->peer);
-      CUDA_CHECK(cudaGetLastError());
-      st->launches += 1;
-    }
-    if (!single) {
+// Pass A over elements [off, off+len).  row0 = partial rows written by earlier chunks of this
+// sweep; final: this launch folds all rows and carries on to the exchange / state step.
+static int launch_pass_a(NKA st, const UpdateShape& u, double* f, size_t off, size_t len, int grid_cap, int row0, bool final)
+{
+  int grid = grid_for(st, occupancy_a(st, u.NC, u.V), len, u.V, NKA_THREADS_A);
+  if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
+  NKA_REQUIRE(row0 + grid <= st->max_grid, "pass A: too many partial rows");
+  double* rows = st->partials + (size_t)row0 * 2 * u.NC;
+  SpanScope t(st, T_PASS_A);
+  nka_get_pass_a(u.NC, u.V)<<<grid, NKA_THREADS_A, 0, st->stream>>>(
+      f + off, st->W + off, st->ld, len, st->S, rows, st->ticket, st->dots, u.fused ? 1 : 0, st->peer,
+      st->partials, final ? (unsigned)(row0 + grid) : 0u);
+  CUDA_CHECK(cudaGetLastError());
+  st->launches += 1;
+  return grid;
+}
+
+// What sits between the sweeps: the cross-rank sum and the scalar step when they are not fused
+// into pass A, the fix-up for the lazily skipped column, or the bare state step of a first call.
+static void launch_mid(NKA st, const UpdateShape& u, double* f)
+{
+  const size_t n = st->vlen;
+  if (u.L > 0) {
+    if (!u.fused) {
       {
         SpanScope t(st, T_COMM);
         const int rc = g_nccl.AllReduce(st->dots, st->dots, 2 * NKA_MAXSLOT, kNcclFloat64, kNcclSum, st->comm->comm, st->stream);
@@ -416,7 +447,7 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
       nka_state_kernel<<<1, NKA_STATE_THREADS, 0, st->stream>>>(st->S, st->dots, 1);
       CUDA_CHECK(cudaGetLastError());
       st->launches += 1;
-    } else if (may_skip) {
+    } else if (u.may_skip) {
       // the oldest column was left out of pass A; this exits at once unless a vtol drop
       // (or the s == 0 guard) means it is needed after all
       SpanScope t(st, T_STATE);
@@ -431,30 +462,110 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
     CUDA_CHECK(cudaGetLastError());
     st->launches += 1;
   }
-  {
-    const int nz = nz_expected(st);
-    const int grid = grid_for(st, occupancy_b(st, nz, V), n, V, NKA_THREADS_B);
-    SpanScope t(st, T_PASS_B);
-    nka_get_pass_b(nz, V)<<<grid, NKA_THREADS_B, 0, st->stream>>>(f, st->W, st->Z, st->ld, n, st->S);
-    CUDA_CHECK(cudaGetLastError());
-    st->launches += 1;
-  }
+}
+
+static void launch_pass_b(NKA st, const UpdateShape& u, double* f, size_t off, size_t len)
+{
+  const int grid = grid_for(st, occupancy_b(st, u.nz, u.V), len, u.V, NKA_THREADS_B);
+  SpanScope t(st, T_PASS_B);
+  nka_get_pass_b(u.nz, u.V)<<<grid, NKA_THREADS_B, 0, st->stream>>>(f + off, st->W + off, st->Z + off, st->ld, len, st->S);
+  CUDA_CHECK(cudaGetLastError());
+  st->launches += 1;
+}
+
+static void update_done(NKA st, const UpdateShape& u)
+{
   // list length: the pending slot (if any) became a pair, capacity mvec pairs, plus the new pending slot
-  if (st->pending) st->ub_len = L + 1 < st->mvec + 1 ? L + 1 : st->mvec + 1;
-  else st->ub_len = L + 1;
+  if (st->pending) st->ub_len = u.L + 1 < st->mvec + 1 ? u.L + 1 : st->mvec + 1;
+  else st->ub_len = u.L + 1;
   st->pending = true;
 }
+
+extern "C" void nka_accel_update_dev(NKA st, double* f)
+{
+  NKA_REQUIRE(st != NULL, "nka_accel_update: null handle");
+  NKA_REQUIRE(f != NULL || st->vlen == 0, "nka_accel_update: null vector");
+  DeviceGuard guard(st->device);
+  const UpdateShape u = update_shape(st, f);
+  if (u.L > 0) launch_pass_a(st, u, f, 0, st->vlen, 0, 0, true);
+  launch_mid(st, u, f);
+  launch_pass_b(st, u, f, 0, st->vlen);
+  update_done(st, u);
+}
+
+// Host f: the same two sweeps, cut into chunks and software-pipelined with the PCIe copies.
+//   copy-in stream :  H2D c0 | H2D c1 | H2D c2 | ...
+//   handle's stream:          passA c0| passA c1| ... passA c_last (+ exchange + state) | passB c0 | passB c1 | ...
+//   copy-out stream:                                                                              | D2H c0  | D2H c1 ...
+// The coefficients need every element of f (global reduction), so no byte can return before the
+// last byte has arrived: the floor is (H2D + D2H) of the vector; the sweeps themselves hide
+// behind the copies except for one chunk at each end.
+#ifndef NKA_HOST_CHUNK_BYTES
+#define NKA_HOST_CHUNK_BYTES (64u << 20)
+#endif
+#define NKA_HOST_MAX_CHUNKS 16
 
 extern "C" void nka_accel_update_host(NKA st, double* f)
 {
   NKA_REQUIRE(st != NULL, "nka_accel_update: null handle");
+  NKA_REQUIRE(f != NULL || st->vlen == 0, "nka_accel_update: null vector");
   DeviceGuard guard(st->device);
-  const size_t bytes = st->vlen * sizeof(double);
+  const size_t n = st->vlen;
+  const size_t bytes = n * sizeof(double);
   if (!st->fstage) CUDA_CHECK(cudaMalloc(&st->fstage, bytes ? bytes : 16));
-  CUDA_CHECK(cudaMemcpyAsync(st->fstage, f, bytes, cudaMemcpyHostToDevice, st->stream));
-  nka_accel_update_dev(st, st->fstage);
-  CUDA_CHECK(cudaMemcpyAsync(f, st->fstage, bytes, cudaMemcpyDeviceToHost, st->stream));
-  CUDA_CHECK(cudaStreamSynchronize(st->stream));
+  if (st->host_chunk_bytes == 0) {
+    st->host_chunk_bytes = NKA_HOST_CHUNK_BYTES;
+    if (const char* e = getenv("NKA_HOST_CHUNK_BYTES")) if (atoll(e) >= 128) st->host_chunk_bytes = (size_t)atoll(e);   // tests
+  }
+  size_t nchunk = (bytes + st->host_chunk_bytes - 1) / st->host_chunk_bytes;
+  if (nchunk > NKA_HOST_MAX_CHUNKS) nchunk = NKA_HOST_MAX_CHUNKS;
+  if (nchunk <= 1) {
+    CUDA_CHECK(cudaMemcpyAsync(st->fstage, f, bytes, cudaMemcpyHostToDevice, st->stream));
+    nka_accel_update_dev(st, st->fstage);
+    CUDA_CHECK(cudaMemcpyAsync(f, st->fstage, bytes, cudaMemcpyDeviceToHost, st->stream));
+    CUDA_CHECK(cudaStreamSynchronize(st->stream));
+    return;
+  }
+  if (!st->copy_in) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st->copy_in, cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st->copy_out, cudaStreamNonBlocking));
+    for (int c = 0; c < NKA_HOST_MAX_CHUNKS; ++c) CUDA_CHECK(cudaEventCreateWithFlags(&st->chunk_ev[c], cudaEventDisableTiming));
+    CUDA_CHECK(cudaEventCreateWithFlags(&st->order_ev, cudaEventDisableTiming));
+  }
+  // chunk boundaries: multiples of 16 doubles, so every chunk keeps the columns' 128-byte alignment
+  size_t per = ((n + nchunk - 1) / nchunk + 15) / 16 * 16;
+  size_t off[NKA_HOST_MAX_CHUNKS + 1];
+  int nc = 0;
+  for (size_t o = 0; o < n; o += per) off[nc++] = o;
+  off[nc] = n;
+
+  double* d = st->fstage;
+  const UpdateShape u = update_shape(st, d);
+  // the staging buffer is free once everything queued on the handle's stream has run
+  CUDA_CHECK(cudaEventRecord(st->order_ev, st->stream));
+  CUDA_CHECK(cudaStreamWaitEvent(st->copy_in, st->order_ev, 0));
+  const int grid_cap = st->max_grid / nc;
+  int row0 = 0;
+  for (int c = 0; c < nc; ++c) {
+    const size_t len = off[c + 1] - off[c];
+    CUDA_CHECK(cudaMemcpyAsync(d + off[c], f + off[c], len * sizeof(double), cudaMemcpyHostToDevice, st->copy_in));
+    CUDA_CHECK(cudaEventRecord(st->chunk_ev[c], st->copy_in));
+    CUDA_CHECK(cudaStreamWaitEvent(st->stream, st->chunk_ev[c], 0));
+    if (u.L > 0) row0 += launch_pass_a(st, u, d, off[c], len, grid_cap, row0, c == nc - 1);
+  }
+  launch_mid(st, u, d);
+  for (int c = 0; c < nc; ++c) {
+    const size_t len = off[c + 1] - off[c];
+    launch_pass_b(st, u, d, off[c], len);
+    CUDA_CHECK(cudaEventRecord(st->chunk_ev[c], st->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(st->copy_out, st->chunk_ev[c], 0));
+    CUDA_CHECK(cudaMemcpyAsync(f + off[c], d + off[c], len * sizeof(double), cudaMemcpyDeviceToHost, st->copy_out));
+  }
+  update_done(st, u);
+  // later work on the handle's stream must not overtake the copy-out (it may reuse the staging buffer)
+  CUDA_CHECK(cudaEventRecord(st->order_ev, st->copy_out));
+  CUDA_CHECK(cudaStreamWaitEvent(st->stream, st->order_ev, 0));
+  CUDA_CHECK(cudaStreamSynchronize(st->copy_out));
 }
 
 extern "C" void nka_accel_update(NKA st, double* f)

@@ -3,7 +3,8 @@
 #include <stddef.h>
 #include "nka_state.h"
 
-typedef void (*PassAFn)(const double*, const double*, size_t, size_t, NkaDevState*, double*, unsigned*, double*, int, NkaPeerCtx*);
+typedef void (*PassAFn)(const double*, const double*, size_t, size_t, NkaDevState*, double*, unsigned*, double*, int, NkaPeerCtx*,
+                        const double*, unsigned);
 typedef void (*PassBFn)(double*, double*, double*, size_t, size_t, const NkaDevState*);
 
 #ifndef NKA_INSTANTIATE_MAX

@@ -142,9 +142,15 @@ __device__ __forceinline__ double nka_warp_sum(double v)
 // a given grid).  Returns true in every thread of that last CTA, after out(j, v)
 // has been called for each j.  Atomic-free except for the ticket.
 // ---------------------------------------------------------------------------
+//
+// A sweep may be cut into several launches over consecutive chunks of the vector (the
+// host-pointer path overlaps them with the PCIe copy of the next chunk): each launch writes its
+// rows at `partials`, and only the final one (fold_rows > 0) takes tickets and folds all
+// fold_rows rows starting at fold_base, earlier launches' rows included (same stream: complete).
 template <int K, int THREADS, typename Out>
 __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* __restrict__ partials,
-                                                unsigned* __restrict__ ticket, Out out)
+                                                unsigned* __restrict__ ticket, const double* __restrict__ fold_base,
+                                                unsigned fold_rows, Out out)
 {
   __shared__ double red[THREADS / 32][K];
   __shared__ bool is_last;
@@ -161,6 +167,7 @@ __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* 
     for (int w = 0; w < THREADS / 32; ++w) v += red[w][threadIdx.x];
     partials[(size_t)blockIdx.x * K + threadIdx.x] = v;
   }
+  if (fold_rows == 0) return false;
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -172,7 +179,7 @@ __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* 
   __threadfence();
   for (int j = warp; j < K; j += THREADS / 32) {
     double v = 0.0;
-    for (unsigned b = lane; b < gridDim.x; b += 32) v += __ldcg(&partials[(size_t)b * K + j]);
+    for (unsigned b = lane; b < fold_rows; b += 32) v += __ldcg(&fold_base[(size_t)b * K + j]);
     v = nka_warp_sum(v);
     if (lane == 0) out(j, v);
   }
@@ -329,7 +336,8 @@ template <int NC, int V>
 __global__ void __launch_bounds__(NKA_THREADS_A, NKA_MINB_A)
 nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld, size_t n,
            NkaDevState* __restrict__ S, double* __restrict__ partials, unsigned* __restrict__ ticket,
-           double* __restrict__ dots, int fuse_state, NkaPeerCtx* __restrict__ peer)
+           double* __restrict__ dots, int fuse_state, NkaPeerCtx* __restrict__ peer,
+           const double* __restrict__ fold_base, unsigned fold_rows)
 {
   const int ncol = S->planA.ncol - S->planA.skip_last;      // columns actually streamed
   const unsigned submask = S->planA.submask;
@@ -355,7 +363,8 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
 
   __shared__ NkaStateStage sm;     // used by the last CTA only
   __shared__ double xv[2 * NC];
-  const bool last = nka_grid_reduce<2 * NC, NKA_THREADS_A>(acc, partials, ticket, [&](int j, double v) { xv[j] = v; });
+  const bool last = nka_grid_reduce<2 * NC, NKA_THREADS_A>(acc, partials, ticket, fold_base, fold_rows,
+                                                         [&](int j, double v) { xv[j] = v; });
   if (!last) return;
   // multi-GPU on one NVLink domain: sum over the ranks right here, through peer memory
   if (peer) nka_peer_allreduce(peer, xv, 2 * NC);

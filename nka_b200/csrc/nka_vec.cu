@@ -90,7 +90,7 @@ nka_vec_dot_kernel(const double* __restrict__ x, const double* __restrict__ y, s
     acc[0] = fma(a.y, b.y, acc[0]);
   }
   if ((n & 1) && start == 0) acc[0] = fma(x[n - 1], y[n - 1], acc[0]);
-  nka_grid_reduce<1, NKA_THREADS>(acc, partials, ticket, [&](int, double v) { out[0] = v; });
+  nka_grid_reduce<1, NKA_THREADS>(acc, partials, ticket, partials, gridDim.x, [&](int, double v) { out[0] = v; });
 }
 
 // ---- life cycle ------------------------------------------------------------------------

@@ -112,6 +112,72 @@ def test_host_pointer_drop_in_path():
     lib.nka_delete(h)
 
 
+_CHUNKED_HOST = r"""
+import sys, numpy as np
+sys.path.insert(0, %(root)r); sys.path.insert(0, %(root)r + "/tests")
+import scenarios as S
+from oracle import api
+from nka_b200 import _lib
+lib = _lib.load()
+for name in ("odd_n1023_m7", "picard_n500_m5_v2", "mixed_n257_m5", "iid_n1000_m10"):
+    n, mvec, vtol, mk = S.SCENARIOS[name]
+    ops = mk()
+    inputs = [op[1] for op in ops if op[0] == "update"]
+    serial, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=0), ops)
+    arbiter, nv = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=1), ops)
+    scales, tols = S.tolerances(serial, arbiter, inputs)
+    h = lib.nka_init(n, mvec, vtol, None)
+    it = 0
+    for k, op in enumerate(ops):
+        if op[0] == "update":
+            got = op[1].copy()
+            lib.nka_accel_update(h, got.ctypes.data)
+            err = np.linalg.norm(got - arbiter[it]) / scales[it]
+            assert err <= tols[it], (name, it, err, tols[it])
+            it += 1
+        elif op[0] == "relax":
+            lib.nka_relax(h)
+        else:
+            lib.nka_restart(h)
+        assert lib.nka_num_vec(h) == nv[k], (name, k)
+    assert lib.nka_defined(h)
+    lib.nka_delete(h)
+print("chunked host path ok")
+"""
+
+
+def test_host_pointer_path_pipelined_in_chunks():
+    """The host-pointer path cuts both sweeps into chunks overlapped with the PCIe copies
+    (nka_capi.cu: nka_accel_update_host).  Force many tiny chunks (256 B: 32 doubles each, up to 16
+    chunks) so small scenarios -- drops, relax/restart, odd tails -- go through the chunked launches,
+    the multi-launch partial-row fold and the per-chunk materialise."""
+    env = dict(os.environ, NKA_HOST_CHUNK_BYTES="256")
+    r = subprocess.run([sys.executable, "-c", _CHUNKED_HOST % {"root": ROOT}], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "chunked host path ok" in r.stdout
+
+
+def test_host_pointer_path_large_pinned_matches_device_path():
+    """n = 2^24 + 3 (two 64 MiB chunks, odd tail) from pinned host memory vs the device-pointer path
+    on the same inputs: same decisions, results equal to reduction-order rounding."""
+    from nka_b200 import NKA
+    torch = _torch()
+    n, mvec = (1 << 24) + 3, 3
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a, b = NKA(n, mvec, 0.01), NKA(n, mvec, 0.01)
+    host = torch.empty(n, dtype=torch.float64, pin_memory=True)
+    for t in range(mvec + 3):
+        f = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) - 0.5
+        host.copy_(f)
+        a.accel_update(f)
+        b.accel_update(host)                     # CPU tensor: nka_accel_update_host
+        got = host.cuda()
+        assert float((got - f).norm() / f.norm()) <= 1e-13, t
+        assert a.num_vec() == b.num_vec()
+    a.delete(); b.delete()
+
+
 def test_device_pointer_autodetected_by_drop_in_entry():
     from nka_b200 import _lib
     lib = _lib.load()
