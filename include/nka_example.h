@@ -78,6 +78,8 @@ int nka_example_solve (NKASYS, NKA acc, int nsweep, double omega, int maxitr, do
 
 /* Device timing with CUDA events on the system's stream: which 0 = pc_ssor (all sweeps of a
  * call), 1 = residual.  Same protocol as nka_timing_*. */
+/* Tuning aid: per-strip timeline of the last SSOR sweep (see nka_example.cu). Returns nstrips. */
+int nka_system_ssor_trace (NKASYS, int on, unsigned long long *out);
 void nka_system_timing_enable (NKASYS, int on);
 void nka_system_timing_read (NKASYS, double ms[2], unsigned long long count[2]);
 unsigned long long nka_system_launch_count (NKASYS);

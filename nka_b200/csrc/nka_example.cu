@@ -9,7 +9,7 @@
 //   ex_ssor_sweep<DIR>   one Gauss-Seidel/SOR sweep in the reference's lexicographic order
 //                        (DIR=+1 forward, -1 backward), src-F08/nka_example.F90:159-175, as a
 //                        pipelined anti-diagonal wavefront: one thread per grid column, one warp
-//                        per strip of 32 columns, neighbouring strips hand over their edge values
+//                        (= one CTA) per strip of 32 columns, neighbouring strips hand over their edge values
 //                        through a flag-in-data channel in L2.  Latency bound: the chain
 //                        z(j-1,k) -> z(j,k) is serial by definition of the method.
 //   ex_permute_kernel    natural order <-> wavefront-major (I/O only).
@@ -50,6 +50,15 @@ EX_HD long long wf_base(int t, int nx, int ny)         // index of cell (j, t-j)
 {
   const int jm = t - (ny - 1);
   return wf_off(t, nx, ny) - (jm > 0 ? jm : 0);
+}
+
+// wf_base(t+1) - wf_base(t) for 0 <= t <= nx+ny-3: lets a walk along consecutive diagonals
+// update its base with a few integer operations instead of re-evaluating wf_base
+EX_HD int wf_step(int t, int nx, int ny)
+{
+  const int jmax = t < nx - 1 ? t : nx - 1;
+  const int over = t - (ny - 1);                    // jmin(t) = max(0, over); jmin(t+1) - jmin(t) = (over >= 0)
+  return jmax - (over > 0 ? over : 0) + (over >= 0 ? 0 : 1);
 }
 
 // ---------------------------------------------------------------------------
@@ -180,14 +189,22 @@ __global__ void ex_fill_u64(unsigned long long* p, size_t n, unsigned long long 
 // ---------------------------------------------------------------------------
 // SSOR sweep
 // ---------------------------------------------------------------------------
-#ifndef EX_SSOR_WARPS
-#define EX_SSOR_WARPS 8          // strips (warps) per CTA
-#endif
-#ifndef EX_SSOR_RING
-#define EX_SSOR_RING 8           // own-cell operands are loaded RING-1 steps ahead of use
-#endif
-#ifndef EX_SSOR_DB
-#define EX_SSOR_DB 3             // edge values from the neighbouring strip are polled DB steps ahead
+// One CTA = one warp = one strip of 32 grid columns; lane l walks column j0 + l down (forward)
+// or up (backward) one row per step, so at any step the 32 lanes sit on ONE anti-diagonal t
+// (warp-uniform: all index arithmetic on t is done once per warp, from blockIdx-derived values)
+// and read/write 32 consecutive doubles of the wavefront-major arrays.
+//
+// The sweep is a chain of dependent cells, so what matters is the latency of one step, i.e. the
+// number of instructions between receiving the upstream value and producing this cell's:
+//   * operands are copied EX_SSOR_DIST steps ahead of use into a shared-memory ring (cp.async,
+//     retired in order with wait_group: see ssor_issue);
+//   * everything that does not depend on new values is formed one step ahead (ssor_cook;
+//     products are rounded separately from the sums, so forming them early is bit-identical):
+//     forward axr*z_old(j+1,k), ayu*z_old(j,k+1), (1-w)*z_old; backward r + axl*z_old(j-1,k)
+//     (the first sum has no new operand), ayd*z_old(j,k-1), (1-w)*z_old;
+//   * per step what is left is the reference's chain: 4 adds, 2-3 multiplies, one division.
+#ifndef EX_SSOR_UNROLL
+#define EX_SSOR_UNROLL 4
 #endif
 // "not written yet" mark of the edge channel: a signalling-NaN bit pattern arithmetic never produces
 #define EX_SENT 0x7FF4DEADBEEF1234ULL
@@ -200,133 +217,292 @@ struct SsorParams {
   unsigned long long* bnd;       // [nstrips][ny]: edge column of strip s, all EX_SENT between sweeps
   double omega, om1;
   int* err;
+  unsigned long long* trace;     // debugging aid (nka_system_ssor_trace): [nstrips][4] globaltimer stamps, or nullptr
 };
 
+// Raw operands of cell (j, tt - j): own r, ac, left/lower face, own old z; the right face (the left
+// face of cell (j+1,k), or the boundary face); the old z of the downstream horizontal neighbour.
 struct SsorEnt { double r, ac, axl, ayd, zo, zs, axr; };
 
-// Operands of cell (j, tt - j): own r, ac, left/lower face, own old z; the right face (the left
-// face of cell (j+1,k), or the boundary face); the old z of the downstream horizontal neighbour.
+// What a step needs that does not depend on new values, formed one step ahead of use from raw
+// operands that were loaded RING steps ahead (so neither the loads nor these products sit on
+// the dependent chain).  forward: a = r, b = axl, p0 = axr*z_old(j+1,k), p1 = ayu*z_old(j,k+1);
+// backward: a = r + axl*z_old(j-1,k), b = axr, p0 = ayd*z_old(j,k-1), p1 unused.
+struct SsorCooked { double a, b, p0, p1, po, ayd, ac; };
+
 template <int DIR>
-__device__ __forceinline__ SsorEnt ssor_load(const SsorParams& P, int tt, int j, bool jvalid)
+__device__ __forceinline__ SsorCooked ssor_cook(const SsorEnt& cur, const SsorEnt& nxt, bool top, double ayt, double om1)
 {
-  SsorEnt e = {0.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-  const int k = tt - j;
-  if (jvalid && k >= 0 && k < P.ny) {
-    const long long c = wf_base(tt, P.nx, P.ny) + j;
-    e.r = __ldg(P.R + c);
-    e.ac = __ldg(P.AC + c);
-    e.axl = __ldg(P.AXL + c);
-    e.ayd = __ldg(P.AYD + c);
-    e.axr = (j + 1 < P.nx) ? __ldg(P.AXL + wf_base(tt + 1, P.nx, P.ny) + j + 1) : __ldg(P.AXR + k);
-    if (!P.zero_old) {
-      e.zo = P.Z[c];
-      const int jj = j + DIR;
-      if (jj >= 0 && jj < P.nx) e.zs = P.Z[wf_base(tt + DIR, P.nx, P.ny) + jj];
-    }
+  SsorCooked c;
+  c.po = __dmul_rn(om1, cur.zo);
+  c.ayd = cur.ayd;
+  c.ac = cur.ac;
+  if (DIR > 0) {
+    c.a = cur.r;
+    c.b = cur.axl;
+    c.p0 = __dmul_rn(cur.axr, cur.zs);
+    c.p1 = __dmul_rn(top ? ayt : nxt.ayd, nxt.zo);          // nxt = (j, k+1); beyond the top: ayt * 0
+  } else {
+    c.a = __dadd_rn(cur.r, __dmul_rn(cur.axl, cur.zs));
+    c.b = cur.axr;
+    c.p0 = __dmul_rn(cur.ayd, nxt.zo);                       // nxt = (j, k-1); below the bottom: ayd * 0
+    c.p1 = 0.0;
   }
+  return c;
+}
+
+// Operand staging: cp.async (LDGSTS, 8 bytes per lane per array) into a shared-memory ring,
+// EX_SSOR_DIST steps ahead of use, retired in order with cp.async.wait_group.  Register-ring
+// prefetching with plain loads does not work here: the warp issues in order and has six load
+// scoreboards for ~60 loads in flight, so a wait for an old load also waits for young ones that
+// share its scoreboard (ncu: 36 % of the issue slots stalled on long_scoreboard, profiles/r1h_*).
+#ifndef EX_SSOR_DIST
+#define EX_SSOR_DIST 15
+#endif
+#define EX_SSOR_STAGES (EX_SSOR_DIST + 1)
+enum { SS_R = 0, SS_AC, SS_AXL, SS_AYD, SS_AXR, SS_ZO, SS_ZS, SS_NF };
+
+__device__ __forceinline__ unsigned long long ex_globaltimer()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// The edge channel lives in L2 and is only ever shared between SMs of this GPU: gpu-scope relaxed
+// accesses (volatile would be system scope).
+__device__ __forceinline__ unsigned long long ch_ld(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void ch_st(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void ss_cp8(uint32_t dst, const double* src, bool on)
+{
+  const int nbytes = on ? 8 : 0;                  // 0: nothing is read, the 8 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(src), "r"(nbytes) : "memory");
+}
+
+// Issue the copies for cell (j, tt - j) into ring stage `stage`.  bc, bn, bp: wf_base of diagonals
+// tt, tt+1, tt-1 (warp-uniform).  Cells outside the grid get zeros (z = 0 there).
+template <int DIR>
+__device__ __forceinline__ void ssor_issue(const SsorParams& P, uint32_t ring, int stage, int tt, long long bc,
+                                           long long bn, long long bp, int j, bool jvalid, int lane)
+{
+  const int k = tt - j;
+  const bool on = jvalid && k >= 0 && k < P.ny;
+  const long long c = on ? bc + j : 0;
+  const uint32_t dst = ring + (uint32_t)((stage * SS_NF * 32 + lane) * 8);
+  ss_cp8(dst + SS_R * 256, P.R + c, on);
+  ss_cp8(dst + SS_AC * 256, P.AC + c, on);
+  ss_cp8(dst + SS_AXL * 256, P.AXL + c, on);
+  ss_cp8(dst + SS_AYD * 256, P.AYD + c, on);
+  const bool inner = j + 1 < P.nx;
+  ss_cp8(dst + SS_AXR * 256, (on && inner) ? P.AXL + bn + j + 1 : P.AXR + (on ? k : 0), on);
+  const bool zon = on && !P.zero_old;
+  ss_cp8(dst + SS_ZO * 256, P.Z + c, zon);
+  if (DIR > 0) ss_cp8(dst + SS_ZS * 256, P.Z + (zon && inner ? bn + j + 1 : 0), zon && inner);   // old z(j+1,k)
+  else ss_cp8(dst + SS_ZS * 256, P.Z + (zon && j > 0 ? bp + j - 1 : 0), zon && j > 0);           // old z(j-1,k)
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ SsorEnt ssor_fetch(const double* ring, int stage, int lane)
+{
+  const double* p = ring + stage * SS_NF * 32 + lane;
+  SsorEnt e;
+  e.r = p[SS_R * 32]; e.ac = p[SS_AC * 32]; e.axl = p[SS_AXL * 32]; e.ayd = p[SS_AYD * 32];
+  e.axr = p[SS_AXR * 32]; e.zo = p[SS_ZO * 32]; e.zs = p[SS_ZS * 32];
   return e;
 }
 
-__device__ __noinline__ unsigned long long ssor_wait(volatile unsigned long long* p, int* err)
+// The edge values of the upstream strip reach the compute warp through a second, helper warp:
+// polling L2 from the compute warp itself puts an L2 round trip (or, with polls issued ahead,
+// the in-order warp's load-scoreboard aliasing: two of every four steps stalled ~450 ns,
+// profiles/r1h_ssor_trace.txt) on the dependent chain.  The helper polls 32 rows at a time,
+// re-arms each channel word for the next sweep, and drops the values into a 64-entry mailbox in
+// shared memory; the compute warp's edge lane picks them up with a ~30-cycle shared-memory load.
+#define EX_MBOX 64
+__device__ __forceinline__ unsigned long long mbox_ld(const unsigned long long* p)
 {
-  const long long t0 = clock64();
-  unsigned it = 0;
-  for (;;) {
-    const unsigned long long v = *p;
-    if (v != EX_SENT) return v;
-    if ((++it & 63u) == 0u) {
-      if (*(volatile int*)err) return 0ull;
-      if (clock64() - t0 > EX_SPIN_LIMIT) { *(volatile int*)err = 1; return 0ull; }
+  return *reinterpret_cast<const volatile unsigned long long*>(p);
+}
+__device__ __forceinline__ void mbox_st(unsigned long long* p, unsigned long long v)
+{
+  *reinterpret_cast<volatile unsigned long long*>(p) = v;
+}
+
+template <int DIR>
+__device__ __forceinline__ void ssor_receiver(const SsorParams& P, unsigned long long* mbox, unsigned long long* cin,
+                                              const int lane)
+{
+  const int ny = P.ny;
+  for (int rb = 0; rb < ny; rb += 32) {
+    const int ri = rb + lane;                      // ri-th row in travel order
+    const int k = DIR > 0 ? ri : ny - 1 - ri;
+    bool done = ri >= ny;
+    unsigned long long v = EX_SENT;
+    const long long t0 = clock64();
+    unsigned it = 0;
+    while (!__all_sync(0xffffffffu, done)) {
+      if (!done) {
+        if (v == EX_SENT) {
+          v = ch_ld(cin + k);
+          if (v != EX_SENT) ch_st(cin + k, EX_SENT);                     // ready for the next sweep
+        }
+        if (v != EX_SENT && mbox_ld(mbox + (ri & (EX_MBOX - 1))) == EX_SENT) {
+          mbox_st(mbox + (ri & (EX_MBOX - 1)), v);
+          done = true;
+        }
+      }
+      if ((++it & 255u) == 0u) {
+        if (*(volatile int*)P.err) return;
+        if (clock64() - t0 > EX_SPIN_LIMIT) { *(volatile int*)P.err = 1; return; }
+      }
     }
   }
 }
 
-template <int DIR>
-__device__ __forceinline__ void ssor_strip(const SsorParams& P, const int strip, const int lane)
+__device__ __noinline__ unsigned long long ssor_mbox_wait(unsigned long long* slot, int* err)
 {
-  constexpr int RING = EX_SSOR_RING, DB = EX_SSOR_DB;
+  unsigned it = 0;
+  for (;;) {
+    const unsigned long long v = mbox_ld(slot);
+    if (v != EX_SENT) return v;
+    if ((++it & 1023u) == 0u && *(volatile int*)err) return 0ull;        // the receiver gave up: so do we
+  }
+}
+
+template <int DIR>
+__device__ __forceinline__ void ssor_strip(const SsorParams& P, double* ring_ptr, unsigned long long* mbox,
+                                           const int strip, const int lane)
+{
+  constexpr int DIST = EX_SSOR_DIST, STAGES = EX_SSOR_STAGES, UNROLL = EX_SSOR_UNROLL;
+  static_assert(DIST >= 3, "ring geometry");
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(ring_ptr);
   const int nx = P.nx, ny = P.ny;
-  const int j = strip * 32 + lane;
-  const bool jvalid = j < nx;
   const int j0 = strip * 32;
+  const int j = j0 + lane;
+  const bool jvalid = j < nx;
   const int jlast = j0 + 31 < nx - 1 ? j0 + 31 : nx - 1;
   const int nsteps = (jlast - j0) + ny;
   const int t_first = DIR > 0 ? j0 : jlast + ny - 1;
   const double ayt = jvalid ? __ldg(P.AYT + j) : 0.0;
-  const double omega = P.omega, om1 = P.om1;
+  const double omega = P.omega;
   // forward: lane 31 hands z(j,k) to lane 0 of the next strip; backward: lane 0 to lane 31 of the previous one
   const bool is_prod = jvalid && (DIR > 0 ? (lane == 31 && j + 1 < nx) : (lane == 0 && strip > 0));
   const bool is_cons = jvalid && (DIR > 0 ? (lane == 0 && strip > 0) : (lane == 31 && j + 1 < nx));
-  volatile unsigned long long* cout = P.bnd + (size_t)strip * ny;
-  volatile unsigned long long* cin = P.bnd + (size_t)(DIR > 0 ? (strip > 0 ? strip - 1 : 0) : (strip + 1 < P.nstrips ? strip + 1 : strip)) * ny;
+  unsigned long long* cout = P.bnd + (size_t)strip * ny;
 
-  SsorEnt q[RING];
-  unsigned long long zb[RING];
-#pragma unroll
-  for (int i = 0; i < RING; ++i) {
-    q[i] = ssor_load<DIR>(P, t_first + DIR * i, j, jvalid);
-    zb[i] = 0ull;
-  }
-#pragma unroll
-  for (int i = 0; i < DB; ++i) {
-    const int kk = t_first + DIR * i - j;
-    if (is_cons && kk >= 0 && kk < ny) zb[i] = cin[kk];
-  }
+  // rolling window of diagonal bases around the prefetch diagonal tp: behind (tp - DIR), at, ahead (tp + DIR)
+  int tp = t_first;
+  long long b_behind = wf_base(tp - DIR, nx, ny), b_at = wf_base(tp, nx, ny), b_ahead = wf_base(tp + DIR, nx, ny);
+  const long long b_first = b_at;
+  int pstage = 0;                                   // ring stage of step number (tp - t_first) * DIR
+  auto issue_next = [&]() {
+    ssor_issue<DIR>(P, ring, pstage, tp, b_at, DIR > 0 ? b_ahead : b_behind, DIR > 0 ? b_behind : b_ahead, j, jvalid, lane);
+    pstage = pstage + 1 == STAGES ? 0 : pstage + 1;
+    tp += DIR;
+    b_behind = b_at; b_at = b_ahead;
+    b_ahead += DIR > 0 ? wf_step(tp, nx, ny) : -wf_step(tp - 1, nx, ny);      // now wf_base(tp + DIR)
+  };
+  __syncwarp();                                     // the previous strip's reads of the ring are done
+  if (P.trace && lane == 0) P.trace[strip * 4 + 0] = ex_globaltimer();
+  for (int i = 0; i < DIST; ++i) issue_next();      // steps 0 .. DIST-1 in flight
 
+  asm volatile("cp.async.wait_group %0;" :: "n"(DIST - 2) : "memory");          // steps 0 and 1 have landed
+  SsorEnt e1 = ssor_fetch(ring_ptr, 1, lane);
+  SsorCooked ck;
+  {
+    const SsorEnt e0 = ssor_fetch(ring_ptr, 0, lane);
+    ck = ssor_cook<DIR>(e0, e1, (t_first - j) + 1 >= ny, ayt, P.om1);
+  }
   double znew = 0.0;        // own result of the previous step = z(j, k-DIR), new
   double ayd_prev = 0.0;    // backward: lower face of the previous step's cell = upper face of this one
-  for (int sb = 0; sb < nsteps; sb += RING) {
+  long long b_cur = b_first;   // wf_base of the current step's diagonal (for the store)
+  int fstage = 2;           // ring stage of step s + 2
+  for (int sb = 0; sb < nsteps; sb += UNROLL) {
 #pragma unroll
-    for (int s = 0; s < RING; ++s) {
-      const int t = t_first + DIR * (sb + s);
+    for (int u = 0; u < UNROLL; ++u) {
+      const int t = t_first + DIR * (sb + u);
       const int k = t - j;
       const bool act = jvalid && k >= 0 && k < ny;
-      const SsorEnt cur = q[s];
-      const SsorEnt& nxt = q[(s + 1) % RING];
       // upstream horizontal neighbour, new value: the adjacent lane's previous step
-      __syncwarp();
       double zh = DIR > 0 ? __shfl_up_sync(0xffffffffu, znew, 1) : __shfl_down_sync(0xffffffffu, znew, 1);
       if (DIR > 0 ? lane == 0 : lane == 31) zh = 0.0;                    // grid edge: boundary value 0
       if (is_cons && act) {
-        unsigned long long v = zb[s];
-        if (v == EX_SENT) v = ssor_wait(cin + k, P.err);
+        // the edge lane's rows are its steps 0 .. ny-1, in travel order
+        unsigned long long* slot = mbox + ((sb + u) & (EX_MBOX - 1));
+        unsigned long long v = mbox_ld(slot);
+        if (v == EX_SENT) { v = ssor_mbox_wait(slot, P.err); if (P.trace) P.trace[strip * 4 + 3] += 1; }
+        mbox_st(slot, EX_SENT);                                          // free for the receiver
         zh = __longlong_as_double((long long)v);
-        cin[k] = EX_SENT;                                                // ready for the next sweep
+        if (P.trace && sb + u == 0) P.trace[strip * 4 + 1] = ex_globaltimer();
       }
-      const double zvo = nxt.zo;                                         // old z(j, k+DIR); 0 outside the grid
-      const double ayu = (k + 1 < ny) ? (DIR > 0 ? nxt.ayd : ayd_prev) : ayt;
-      const double zl = DIR > 0 ? zh : cur.zs, zr = DIR > 0 ? cur.zs : zh;
-      const double zd = DIR > 0 ? znew : zvo, zu = DIR > 0 ? zvo : znew;
-      // src-F08/nka_example.F90:163-165 (= :171-173), the reference's operation order, no fma
-      double sm = __dadd_rn(cur.r, __dmul_rn(cur.axl, zl));
-      sm = __dadd_rn(sm, __dmul_rn(cur.axr, zr));
-      sm = __dadd_rn(sm, __dmul_rn(cur.ayd, zd));
-      sm = __dadd_rn(sm, __dmul_rn(ayu, zu));
-      const double zc = __dadd_rn(__dmul_rn(om1, cur.zo), __ddiv_rn(__dmul_rn(omega, sm), cur.ac));
+      // src-F08/nka_example.F90:163-165 (= :171-173): the reference's operation order, no fma
+      //   z = (1-w) z + w (r + axl z(j-1,k) + axr z(j+1,k) + ayd z(j,k-1) + ayu z(j,k+1)) / ac
+      double sm;
+      if (DIR > 0) {
+        sm = __dadd_rn(ck.a, __dmul_rn(ck.b, zh));                       // r + axl * new left
+        sm = __dadd_rn(sm, ck.p0);                                       //   + axr * old right
+        sm = __dadd_rn(sm, __dmul_rn(ck.ayd, znew));                     //   + ayd * new lower
+        sm = __dadd_rn(sm, ck.p1);                                       //   + ayu * old upper
+      } else {
+        const double ayu = (k + 1 < ny) ? ayd_prev : ayt;
+        sm = __dadd_rn(ck.a, __dmul_rn(ck.b, zh));                       // (r + axl * old left) + axr * new right
+        sm = __dadd_rn(sm, ck.p0);                                       //   + ayd * old lower
+        sm = __dadd_rn(sm, __dmul_rn(ayu, znew));                        //   + ayu * new upper
+      }
+      // (cells outside the grid divide 1 by 1: a zero numerator would take the division's slow path
+      // for the whole warp during the 31 fill / drain steps of every strip)
+      const double zc = __dadd_rn(ck.po, __ddiv_rn(act ? __dmul_rn(omega, sm) : 1.0, act ? ck.ac : 1.0));
       if (act) {
         znew = zc;
-        ayd_prev = cur.ayd;
-        P.Z[wf_base(t, nx, ny) + j] = zc;
-        if (is_prod) cout[k] = (unsigned long long)__double_as_longlong(zc);
+        ayd_prev = ck.ayd;
+        P.Z[b_cur + j] = zc;
+        if (is_prod) ch_st(cout + k, (unsigned long long)__double_as_longlong(zc));
       }
-      q[s] = ssor_load<DIR>(P, t + DIR * RING, j, jvalid);
-      {
-        const int kk = t + DIR * DB - j;
-        zb[(s + DB) % RING] = (is_cons && kk >= 0 && kk < ny) ? cin[kk] : 0ull;
-      }
+      if (P.trace && strip == P.nstrips / 2 && lane == 0 && sb + u < 256) P.trace[P.nstrips * 4 + sb + u] = ex_globaltimer();
+      b_cur += DIR > 0 ? wf_step(t, nx, ny) : -wf_step(t - 1, nx, ny);
+      // off the chain: issue the operands DIST steps ahead, retire the copies of step s + 2,
+      // and form the next step's independent terms
+      issue_next();
+      asm volatile("cp.async.wait_group %0;" :: "n"(DIST - 2) : "memory");
+      const SsorEnt e2 = ssor_fetch(ring_ptr, fstage, lane);
+      fstage = fstage + 1 == STAGES ? 0 : fstage + 1;
+      ck = ssor_cook<DIR>(e1, e2, (k + DIR) + 1 >= ny, ayt, P.om1);
+      e1 = e2;
     }
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  if (P.trace && lane == 0) P.trace[strip * 4 + 2] = ex_globaltimer();
 }
 
 template <int DIR>
-__global__ void __launch_bounds__(EX_SSOR_WARPS * 32, 1) ex_ssor_sweep(SsorParams P)
+__global__ void __launch_bounds__(64) ex_ssor_sweep(SsorParams P)
 {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int slots = gridDim.x * EX_SSOR_WARPS;
-  // strips in dependency order: a strip only waits for one that an earlier slot (or an earlier
-  // round of the last slot) owns, and every CTA of the grid is resident, so no wait can deadlock
-  for (int i = blockIdx.x * EX_SSOR_WARPS + warp; i < P.nstrips; i += slots)
-    ssor_strip<DIR>(P, DIR > 0 ? i : P.nstrips - 1 - i, lane);
+  __shared__ __align__(16) double ring[EX_SSOR_STAGES * SS_NF * 32];
+  __shared__ unsigned long long mbox[EX_MBOX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // strips in dependency order: a strip only waits for one that an earlier CTA (or an earlier
+  // round of this grid) owns, and every CTA of the grid is resident, so no wait can deadlock
+  for (int i = blockIdx.x; i < P.nstrips; i += gridDim.x) {
+    const int strip = DIR > 0 ? i : P.nstrips - 1 - i;
+    const bool has_upstream = i > 0 && (DIR > 0 || (strip + 1) * 32 < P.nx + 0);
+    if (threadIdx.x < EX_MBOX) mbox[threadIdx.x] = EX_SENT;
+    __syncthreads();
+    if (warp == 0) {
+      ssor_strip<DIR>(P, ring, mbox, strip, lane);
+    } else if (has_upstream) {
+      // upstream strip: forward strip-1 (its lane 31 writes bnd[strip-1]); backward strip+1 (its lane 0 writes bnd[strip+1])
+      ssor_receiver<DIR>(P, mbox, P.bnd + (size_t)(DIR > 0 ? strip - 1 : strip + 1) * P.ny, lane);
+    }
+    __syncthreads();
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -344,6 +520,7 @@ struct nka_system {
   int cur = 0;
   double *R = nullptr, *Z = nullptr, *AXL = nullptr, *AYD = nullptr, *AC = nullptr, *AXR = nullptr, *AYT = nullptr;
   unsigned long long* bnd = nullptr;
+  unsigned long long* trace = nullptr;   // debugging aid, see nka_system_ssor_trace
   int nstrips = 0;
   double* partials = nullptr;
   unsigned* ticket = nullptr;
@@ -431,12 +608,12 @@ extern "C" NKASYS nka_system_init(int nx, int ny, double a, int scaling, int dev
   CUDA_CHECK(cudaMemsetAsync(sy->result, 0, 2 * sizeof(double), sy->stream));
   CUDA_CHECK(cudaMallocHost(&sy->result_host, 2 * sizeof(double)));
   int occ = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep<1>, EX_SSOR_WARPS * 32, 0));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep<1>, 64, 0));
   int occb = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep<-1>, EX_SSOR_WARPS * 32, 0));
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep<-1>, 64, 0));
   if (occb < occ) occ = occb;
   NKA_REQUIRE(occ >= 1, "nka_system_init: the SSOR kernel does not fit on an SM");
-  const int want = (sy->nstrips + EX_SSOR_WARPS - 1) / EX_SSOR_WARPS;
+  const int want = sy->nstrips;
   const int cap = occ * sy->num_sms;
   sy->ssor_grid = want < cap ? want : cap;
   return sy;
@@ -450,6 +627,7 @@ extern "C" void nka_system_delete(NKASYS sy)
   for (const ExSpan& sp : sy->spans) { cudaEventDestroy(sp.beg); cudaEventDestroy(sp.end); }
   cudaFree(sy->U[0]); cudaFree(sy->U[1]); cudaFree(sy->R); cudaFree(sy->Z); cudaFree(sy->AXL);
   cudaFree(sy->AYD); cudaFree(sy->AC); cudaFree(sy->AXR); cudaFree(sy->AYT); cudaFree(sy->bnd);
+  cudaFree(sy->trace);
   cudaFree(sy->partials); cudaFree(sy->ticket); cudaFree(sy->result); cudaFree(sy->stage);
   cudaFreeHost(sy->result_host);
   delete sy;
@@ -559,17 +737,34 @@ extern "C" int nka_system_pc_ssor(NKASYS sy, int nsweep, double omega)
   P.Z = sy->Z; P.bnd = sy->bnd;
   P.omega = omega; P.om1 = 1.0 - omega;
   P.err = reinterpret_cast<int*>(sy->result + 1);
+  P.trace = sy->trace;
   ExScope t(sy, 0);
   for (int i = 0; i < nsweep; ++i) {
     P.zero_old = (i == 0) ? 1 : 0;                       // z = 0 start (:158): nothing to read yet
-    ex_ssor_sweep<1><<<sy->ssor_grid, EX_SSOR_WARPS * 32, 0, sy->stream>>>(P);
+    ex_ssor_sweep<1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     P.zero_old = 0;
-    ex_ssor_sweep<-1><<<sy->ssor_grid, EX_SSOR_WARPS * 32, 0, sy->stream>>>(P);
+    ex_ssor_sweep<-1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     sy->launches += 2;
   }
   return sy->error;
+}
+
+// Debugging / tuning aid (tools/ssor_trace.py; not part of the reference's interface): with on != 0 the
+// next sweeps record per strip {start, first cell done, end} globaltimer stamps and the number of
+// synchronous waits on the neighbour strip; out (may be NULL) receives nstrips*4 words of the last sweep.
+extern "C" int nka_system_ssor_trace(NKASYS sy, int on, unsigned long long* out)
+{
+  NKA_REQUIRE(sy != NULL, "nka_system_ssor_trace: null handle");
+  DeviceGuard guard(sy->device);
+  const size_t bytes = ((size_t)sy->nstrips * 4 + 256) * sizeof(unsigned long long);
+  CUDA_CHECK(cudaStreamSynchronize(sy->stream));
+  if (out && sy->trace) CUDA_CHECK(cudaMemcpy(out, sy->trace, bytes, cudaMemcpyDeviceToHost));
+  if (on && !sy->trace) CUDA_CHECK(cudaMalloc(&sy->trace, bytes));
+  if (!on && sy->trace) { cudaFree(sy->trace); sy->trace = nullptr; }
+  if (sy->trace) CUDA_CHECK(cudaMemset(sy->trace, 0, bytes));
+  return sy->nstrips;
 }
 
 extern "C" int nka_example_solve(NKASYS sy, NKA acc, int nsweep, double omega, int maxitr, double tol,
