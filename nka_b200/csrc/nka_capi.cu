@@ -167,38 +167,61 @@ struct SpanScope {
   }
 };
 
-static int grid_for(NKA st, int occ, size_t n, int V, int threads = NKA_THREADS)
+static int grid_for(NKA st, int per_sm, size_t n, int V, int threads = NKA_THREADS)
 {
   const size_t nv = n / V;
   size_t need = (nv + threads - 1) / threads;
   if (need < 1) need = 1;
-  size_t full = (size_t)st->num_sms * (occ > 0 ? occ : 1);
+  size_t full = (size_t)st->num_sms * (per_sm > 0 ? per_sm : 1);
   size_t g = need < full ? need : full;
   if (g > (size_t)st->max_grid) g = st->max_grid;
   return (int)g;
 }
 
-static int occupancy_a(NKA st, int nc, int V)
+// CTAs per SM for a sweep over n elements = resident CTAs x waves.  Several waves even out the
+// tail of a long grid-stride sweep (+1 % at n = 2^28 with 8 waves), but every wave costs each SM one
+// more prologue / reduction epilogue and the last CTA one more partial row to fold: at n = 2^25
+// one wave is 2.6 % faster than eight, at 2^24 5.5 % (profiles/r1i_waves_sweep.txt).  So: one
+// wave per ~2^17 double2 per SM.
+static int waves_for(NKA st, size_t n, int V)
+{
+  const size_t per_wave = (size_t)st->num_sms * 113000u;
+  size_t w = (n / V) / per_wave;
+  if (w < 1) w = 1;
+  if (w > NKA_WAVES) w = NKA_WAVES;
+  return (int)w;
+}
+
+static int resident_a(NKA st, int nc, int V)
 {
   if (st->occ_a[nc][V] < 0) {
     int nb = 0;
     NKA_REQUIRE(nka_get_pass_a(nc, V) != nullptr, "pass A is not instantiated for this subspace size in this build");
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nka_get_pass_a(nc, V), NKA_THREADS_A, 0));
-    // several waves of CTAs per SM even out the tail of the grid-stride sweep (profiles/r1c sweep)
-    st->occ_a[nc][V] = g_grid_per_sm_a > 0 ? g_grid_per_sm_a : (nb > 0 ? nb : 1) * NKA_WAVES;
+    st->occ_a[nc][V] = nb > 0 ? nb : 1;
   }
   return st->occ_a[nc][V];
 }
 
-static int occupancy_b(NKA st, int nz, int V)
+static int resident_b(NKA st, int nz, int V)
 {
   if (st->occ_b[nz][V] < 0) {
     int nb = 0;
     NKA_REQUIRE(nka_get_pass_b(nz, V) != nullptr, "pass B is not instantiated for this subspace size in this build");
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nka_get_pass_b(nz, V), NKA_THREADS_B, 0));
-    st->occ_b[nz][V] = g_grid_per_sm_b > 0 ? g_grid_per_sm_b : (nb > 0 ? nb : 1) * NKA_WAVES;
+    st->occ_b[nz][V] = nb > 0 ? nb : 1;
   }
   return st->occ_b[nz][V];
+}
+
+static int per_sm_a(NKA st, int nc, int V, size_t len)
+{
+  return g_grid_per_sm_a > 0 ? g_grid_per_sm_a : resident_a(st, nc, V) * waves_for(st, len, V);
+}
+
+static int per_sm_b(NKA st, int nz, int V, size_t len)
+{
+  return g_grid_per_sm_b > 0 ? g_grid_per_sm_b : resident_b(st, nz, V) * waves_for(st, len, V);
 }
 
 // How many pairs are expected on the list at entry (pass B streams their Z columns): exact
@@ -418,7 +441,7 @@ static UpdateShape update_shape(NKA st, const double* f)
 // sweep; final: this launch folds all rows and carries on to the exchange / state step.
 static int launch_pass_a(NKA st, const UpdateShape& u, double* f, size_t off, size_t len, int grid_cap, int row0, bool final)
 {
-  int grid = grid_for(st, occupancy_a(st, u.NC, u.V), len, u.V, NKA_THREADS_A);
+  int grid = grid_for(st, per_sm_a(st, u.NC, u.V, len), len, u.V, NKA_THREADS_A);
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
   NKA_REQUIRE(row0 + grid <= st->max_grid, "pass A: too many partial rows");
   double* rows = st->partials + (size_t)row0 * 2 * u.NC;
@@ -466,7 +489,7 @@ static void launch_mid(NKA st, const UpdateShape& u, double* f)
 
 static void launch_pass_b(NKA st, const UpdateShape& u, double* f, size_t off, size_t len)
 {
-  const int grid = grid_for(st, occupancy_b(st, u.nz, u.V), len, u.V, NKA_THREADS_B);
+  const int grid = grid_for(st, per_sm_b(st, u.nz, u.V, len), len, u.V, NKA_THREADS_B);
   SpanScope t(st, T_PASS_B);
   nka_get_pass_b(u.nz, u.V)<<<grid, NKA_THREADS_B, 0, st->stream>>>(f + off, st->W + off, st->Z + off, st->ld, len, st->S);
   CUDA_CHECK(cudaGetLastError());
@@ -722,9 +745,9 @@ extern "C" void nka_launch_geometry(NKA st, int* grid_a, int* grid_b, int* threa
   const int L = st->ub_len;
   const bool may_skip = (st->comm == nullptr || st->peer != nullptr) && st->lazy && st->pending && L == st->mvec + 1;
   const int NC = may_skip ? st->mvec : L;
-  if (grid_a) *grid_a = L > 0 ? grid_for(st, occupancy_a(st, NC, 2), st->vlen, 2, NKA_THREADS_A) : 0;
+  if (grid_a) *grid_a = L > 0 ? grid_for(st, per_sm_a(st, NC, 2, st->vlen), st->vlen, 2, NKA_THREADS_A) : 0;
   const int nz = nz_expected(st);
-  if (grid_b) *grid_b = grid_for(st, occupancy_b(st, nz, 2), st->vlen, 2, NKA_THREADS_B);
+  if (grid_b) *grid_b = grid_for(st, per_sm_b(st, nz, 2, st->vlen), st->vlen, 2, NKA_THREADS_B);
   if (threads) *threads = NKA_THREADS_A * 10000 + NKA_THREADS_B;
 }
 

@@ -135,6 +135,29 @@ __device__ __forceinline__ double nka_warp_sum(double v)
   return v;
 }
 
+__device__ __forceinline__ unsigned long long nka_globaltimer()
+{
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---------------------------------------------------------------------------
+// Tuning aid, compiled in only with -DNKA_TRACE (tools/pass_a_trace.py): globaltimer stamps of
+// pass A's phases.  [0] first CTA start (min) [1] last CTA's loop end (max) [2] ticket won
+// [3] partial rows folded [4] exchange done [5] state step committed.
+// ---------------------------------------------------------------------------
+#ifdef NKA_TRACE
+static __device__ unsigned long long g_nka_trace[8];
+#define NKA_STAMP_MIN(i) do { if (threadIdx.x == 0) atomicMin(&g_nka_trace[i], nka_globaltimer()); } while (0)
+#define NKA_STAMP_MAX(i) do { if (threadIdx.x == 0) atomicMax(&g_nka_trace[i], nka_globaltimer()); } while (0)
+#define NKA_STAMP(i) do { if (threadIdx.x == 0) g_nka_trace[i] = nka_globaltimer(); } while (0)
+#else
+#define NKA_STAMP_MIN(i) do { } while (0)
+#define NKA_STAMP_MAX(i) do { } while (0)
+#define NKA_STAMP(i) do { } while (0)
+#endif
+
 // ---------------------------------------------------------------------------
 // Deterministic grid reduction of K per-thread accumulators: shuffle tree inside
 // each warp, fixed-order sum across warps, one partial row per CTA, and the last
@@ -176,6 +199,7 @@ __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* 
   }
   __syncthreads();
   if (!is_last) return false;
+  NKA_STAMP(2);
   __threadfence();
   for (int j = warp; j < K; j += THREADS / 32) {
     double v = 0.0;
@@ -201,12 +225,6 @@ __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* 
 //   that peer's contribution to finish the current one), so the slot written
 //   for exchange e+2 has been consumed by everyone.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long nka_globaltimer()
-{
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 
 __device__ __forceinline__ void nka_peer_allreduce(NkaPeerCtx* __restrict__ P, double* vals, int K)
 {
@@ -339,6 +357,7 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
            double* __restrict__ dots, int fuse_state, NkaPeerCtx* __restrict__ peer,
            const double* __restrict__ fold_base, unsigned fold_rows)
 {
+  NKA_STAMP_MIN(0);
   const int ncol = S->planA.ncol - S->planA.skip_last;      // columns actually streamed
   const unsigned submask = S->planA.submask;
   const double* wcol[NC];
@@ -361,13 +380,16 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
   }
   if (V == 2 && (n & 1) && start == 0) nka_pass_a_elem<NC, 1, false>(f, wcol, n - 1, ncol, submask, acc);
 
+  NKA_STAMP_MAX(1);
   __shared__ NkaStateStage sm;     // used by the last CTA only
   __shared__ double xv[2 * NC];
   const bool last = nka_grid_reduce<2 * NC, NKA_THREADS_A>(acc, partials, ticket, fold_base, fold_rows,
                                                          [&](int j, double v) { xv[j] = v; });
   if (!last) return;
+  NKA_STAMP(3);
   // multi-GPU on one NVLink domain: sum over the ranks right here, through peer memory
   if (peer) nka_peer_allreduce(peer, xv, 2 * NC);
+  NKA_STAMP(4);
   for (int j = threadIdx.x; j < 2 * NC; j += NKA_THREADS_A) {
     const int at = (j < NC) ? j : (NKA_MAXSLOT + (j - NC));
     dots[at] = xv[j];
@@ -381,6 +403,8 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
     for (unsigned i = threadIdx.x; i < sizeof(NkaDevState) / 4; i += blockDim.x) dst[i] = __ldcg(src + i);
     __syncthreads();
     nka_run_state_step(sm, S, /*have_last=*/0);
+    __syncthreads();
+    NKA_STAMP(5);
   }
 }
 

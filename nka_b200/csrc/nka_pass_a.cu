@@ -20,3 +20,14 @@ PassAFn nka_get_pass_a(int nc, int v)
   if (nc < 1 || nc > NKA_MAXSLOT || v < 1 || v > 2) return nullptr;
   return g_pass_a[nc][v];
 }
+
+#ifdef NKA_TRACE
+// tools/pass_a_trace.py (tuning builds only): read and re-arm the phase stamps
+extern "C" void nka_debug_trace(unsigned long long out[8])
+{
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_nka_trace, sizeof(unsigned long long) * 8);
+  unsigned long long init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(g_nka_trace, init, sizeof init);
+}
+#endif

@@ -281,6 +281,12 @@ NKA_HD int nka_state_step(NkaDevState& S, const double* dots, int stride, int ha
     NKA_H(S, p, p) = 1.0;
     const double tol2 = S.vtol * S.vtol;
     int pos = 1;                                   // list position of k as pass A saw it
+    // act[0..na-1] = the slots on the list before k, in list order (p first, then the survivors):
+    // walking it is walking the reference's list (`for j = first; j != k; j = next[j]`) without
+    // the dependent next[] loads, so the operand loads of consecutive terms overlap.
+    int act[NKA_MAXSLOT];
+    int na = 1;
+    act[0] = p;
     for (int k = S.next[p]; k != NKA_NIL; k = S.next[k], ++pos) {
       if (++nvec > S.mvec) {                       // :339-347
         if (S.last != k) S.error = 1;
@@ -295,16 +301,21 @@ NKA_HD int nka_state_step(NkaDevState& S, const double* dots, int stride, int ha
       }
       if (pos == missing) { S.need_fixup = 1; return 1; }   // a drop made room: the skipped column matters
       double hkk = 1.0;                            // :350-360
-      for (int j = p; j != k; j = S.next[j]) {
-        double hkj = NKA_H(S, j, k);
-        for (int i = p; i != j; i = S.next[i]) hkj -= NKA_H(S, k, i) * NKA_H(S, j, i);
-        hkj /= NKA_H(S, j, j);
-        NKA_H(S, k, j) = hkj;
+      const double* hk_raw = &NKA_H(S, 0, k);      // column k: raw Gram entries H(j,k) of newer slots j
+      double* hk = &NKA_H(S, k, 0);                // row k: the factor entries being formed
+      for (int jj = 0; jj < na; ++jj) {
+        const int j = act[jj];
+        const double* hj = &NKA_H(S, j, 0);
+        double hkj = hk_raw[j * NKA_MAXSLOT];
+        for (int ii = 0; ii < jj; ++ii) hkj -= hk[act[ii]] * hj[act[ii]];
+        hkj /= hj[j];
+        hk[j] = hkj;
         hkk -= hkj * hkj;
       }
       if (hkk - tol2 < S.min_margin) S.min_margin = hkk - tol2;
       if (hkk > tol2) {                            // :362-363
         NKA_H(S, k, k) = NKA_SQRT(hkk);
+        act[na++] = k;
       } else {                                     // :364-379
         const int pk = S.prev[k], nk = S.next[k];
         S.next[pk] = nk;
@@ -342,14 +353,20 @@ NKA_HD int nka_state_step(NkaDevState& S, const double* dots, int stride, int ha
   if (S.subspace) {
     for (int j = 0; j < L; ++j)
       if (!removed[ord[j]]) rhs[ord[j]] = fd[j] / S.s[ord[j]];        // <f, w_k>
-    for (int j = S.first; j != NKA_NIL; j = S.next[j]) {
+    int lst[NKA_MAXSLOT];                          // the list after the update, newest first
+    int nl = 0;
+    for (int j = S.first; j != NKA_NIL; j = S.next[j]) lst[nl++] = j;
+    for (int jj = 0; jj < nl; ++jj) {              // forward substitution, :405-411
+      const int j = lst[jj];
+      const double* hj = &NKA_H(S, j, 0);
       double cj = rhs[j];
-      for (int i = S.first; i != j; i = S.next[i]) cj -= NKA_H(S, j, i) * S.c[i];
-      S.c[j] = cj / NKA_H(S, j, j);
+      for (int ii = 0; ii < jj; ++ii) cj -= hj[lst[ii]] * S.c[lst[ii]];
+      S.c[j] = cj / hj[j];
     }
-    for (int j = S.last; j != NKA_NIL; j = S.prev[j]) {
+    for (int jj = nl - 1; jj >= 0; --jj) {         // backward substitution, :412-417
+      const int j = lst[jj];
       double cj = S.c[j];
-      for (int i = S.last; i != j; i = S.prev[i]) cj -= NKA_H(S, i, j) * S.c[i];
+      for (int ii = nl - 1; ii > jj; --ii) cj -= NKA_H(S, lst[ii], j) * S.c[lst[ii]];
       S.c[j] = cj / NKA_H(S, j, j);
     }
     B.write_f = 1;
