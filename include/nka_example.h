@@ -44,6 +44,18 @@ enum {
  * :227-245); scaling 1: the F08 flavours (q = 1, face terms t*hx**2: src-F08/nka_example.F90:100,
  * :131-135).  device < 0: current device.  stream: cudaStream_t or NULL. */
 NKASYS nka_system_init (int nx, int ny, double a, int scaling, int device, void *stream);
+/* Row slabs (one process per GPU; BASELINE.json configs[3]): this handle holds rows [k0, k1) of an
+ * nx x ny_global grid (the reference's parallel recipe: each processing element passes its
+ * portion of the vector, src-F08-vector/README.md:16-22).  nka_system_comm_init is collective;
+ * rank r's slab lies directly above rank r-1's.  The residual then exchanges one row of u with
+ * each neighbour and returns the GLOBAL norm; pc_ssor continues the exact lexicographic sweep
+ * from the rank below (forward) / above (backward), strip by strip, through edge rows written
+ * straight into the neighbour's memory (NVLink peer access), so results stay bit-identical to
+ * the single-GPU and the CPU sweeps.  nka_comm_share_system makes an accelerator created with
+ * vlen = nx*(k1-k0) sum its dot products over the same ranks. */
+NKASYS nka_system_init_slab (int nx, int ny_global, int k0, int k1, double a, int scaling, int device, void *stream);
+int nka_system_comm_init (NKASYS, int nranks, int rank, const void *id128);
+void nka_comm_share_system (NKA, NKASYS);
 void nka_system_delete (NKASYS);
 size_t nka_system_size (NKASYS);                       /* nx*ny */
 void *nka_system_stream (NKASYS);

@@ -80,6 +80,9 @@ SYMBOLS = {
     "nka_b200_version": (C.c_char_p, []),
     # include/nka_example.h
     "nka_system_init": (C.c_void_p, [C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]),
+    "nka_system_init_slab": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]),
+    "nka_system_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "nka_comm_share_system": (None, [C.c_void_p, C.c_void_p]),
     "nka_system_delete": (None, [C.c_void_p]),
     "nka_system_size": (C.c_size_t, [C.c_void_p]),
     "nka_system_stream": (C.c_void_p, [C.c_void_p]),

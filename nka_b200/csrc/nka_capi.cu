@@ -65,6 +65,10 @@ bool nka_nccl_load()
   g_nccl.CommInitRank = (int (*)(void**, int, NkaId128, int))dlsym(g_nccl.lib, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
   g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllGather");
+  g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclSend");
+  g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclRecv");
+  g_nccl.GroupStart = (int (*)())dlsym(g_nccl.lib, "ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())dlsym(g_nccl.lib, "ncclGroupEnd");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
   return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.CommDestroy;
@@ -250,6 +254,59 @@ static void peer_teardown(NKA st)
   cudaGetLastError();
 }
 
+void nka_ipc_unmap(NkaComm* c, void** mapped)
+{
+  for (int r = 0; r < c->nranks; ++r)
+    if (r != c->rank && mapped[r]) { cudaIpcCloseMemHandle(mapped[r]); mapped[r] = nullptr; }
+  cudaGetLastError();
+}
+
+bool nka_ipc_exchange(NkaComm* c, cudaStream_t stream, void* local, void** mapped, const bool* want)
+{
+  const int R = c->nranks, me = c->rank;
+  struct Card { cudaIpcMemHandle_t h; int ok; int pad; };
+  Card mine;
+  memset(&mine, 0, sizeof mine);
+  mine.ok = (local != nullptr && g_nccl.AllGather != nullptr) ? 1 : 0;
+  if (mine.ok && cudaIpcGetMemHandle(&mine.h, local) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+  for (int r = 0; r < R; ++r) mapped[r] = nullptr;
+  if (!g_nccl.AllGather) return false;             // same library on every rank: unanimous
+  Card* d_cards = nullptr;
+  int* d_flag = nullptr;
+  CUDA_CHECK(cudaMalloc(&d_cards, sizeof(Card) * (R + 1)));
+  CUDA_CHECK(cudaMalloc(&d_flag, sizeof(int)));
+  CUDA_CHECK(cudaMemcpyAsync(d_cards + R, &mine, sizeof mine, cudaMemcpyHostToDevice, stream));
+  int rc = g_nccl.AllGather(d_cards + R, d_cards, sizeof(Card), kNcclChar, c->comm, stream);
+  if (rc != 0) nka_fail(__FILE__, __LINE__, "ncclAllGather (IPC handles) failed");
+  std::vector<Card> cards(R);
+  CUDA_CHECK(cudaMemcpyAsync(cards.data(), d_cards, sizeof(Card) * R, cudaMemcpyDeviceToHost, stream));
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  int ok = 1;
+  for (int r = 0; r < R; ++r) ok &= cards[r].ok;
+  if (ok) {
+    mapped[me] = local;
+    for (int r = 0; r < R; ++r) {
+      if (r == me || !want[r]) continue;
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, cards[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+        cudaGetLastError();
+        ok = 0;
+        break;
+      }
+      mapped[r] = p;
+    }
+  }
+  CUDA_CHECK(cudaMemcpyAsync(d_flag, &ok, sizeof ok, cudaMemcpyHostToDevice, stream));
+  rc = g_nccl.AllReduce(d_flag, d_flag, 1, kNcclInt32, kNcclMin, c->comm, stream);
+  if (rc != 0) nka_fail(__FILE__, __LINE__, "ncclAllReduce (IPC agreement) failed");
+  CUDA_CHECK(cudaMemcpyAsync(&ok, d_flag, sizeof ok, cudaMemcpyDeviceToHost, stream));
+  CUDA_CHECK(cudaStreamSynchronize(stream));
+  cudaFree(d_cards);
+  cudaFree(d_flag);
+  if (!ok) { nka_ipc_unmap(c, mapped); mapped[me] = nullptr; return false; }
+  return true;
+}
+
 // Collective over the communicator.  Every rank allocates a box, the IPC handles are
 // all-gathered with NCCL, every rank opens every peer's box, and an all-reduce(min) makes the
 // outcome unanimous: either every rank reduces through peer memory or every rank stays on NCCL.
@@ -261,56 +318,27 @@ static bool peer_setup(NKA st)
   if (const char* e = getenv("NKA_PEER_REDUCE")) if (atoi(e) == 0) return false;    // ablation: NCCL all-reduce
   if (c->nranks < 2 || c->nranks > NKA_MAX_RANKS) return false;
   const int R = c->nranks, me = c->rank;
-  struct Card { cudaIpcMemHandle_t h; int ok; int pad; };
-  Card mine;
-  memset(&mine, 0, sizeof mine);
-  mine.ok = 1;
-  if (cudaMalloc(&st->peer_box, kPeerBoxBytes) != cudaSuccess) { cudaGetLastError(); st->peer_box = nullptr; mine.ok = 0; }
-  if (mine.ok) {
+  if (cudaMalloc(&st->peer_box, kPeerBoxBytes) != cudaSuccess) { cudaGetLastError(); st->peer_box = nullptr; }
+  if (st->peer_box) {
     CUDA_CHECK(cudaMemsetAsync(st->peer_box, 0, kPeerBoxBytes, st->stream));
     CUDA_CHECK(cudaStreamSynchronize(st->stream));
-    if (cudaIpcGetMemHandle(&mine.h, st->peer_box) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
   }
-  Card* d_cards = nullptr;
-  int* d_flag = nullptr;
-  CUDA_CHECK(cudaMalloc(&d_cards, sizeof(Card) * (R + 1)));
-  CUDA_CHECK(cudaMalloc(&d_flag, sizeof(int)));
-  CUDA_CHECK(cudaMemcpyAsync(d_cards + R, &mine, sizeof mine, cudaMemcpyHostToDevice, st->stream));
-  int rc = g_nccl.AllGather(d_cards + R, d_cards, sizeof(Card), kNcclChar, c->comm, st->stream);
-  if (rc != 0) nka_fail(__FILE__, __LINE__, "ncclAllGather (peer box handles) failed");
-  std::vector<Card> cards(R);
-  CUDA_CHECK(cudaMemcpyAsync(cards.data(), d_cards, sizeof(Card) * R, cudaMemcpyDeviceToHost, st->stream));
-  CUDA_CHECK(cudaStreamSynchronize(st->stream));
-  int ok = 1;
-  for (int r = 0; r < R; ++r) ok &= cards[r].ok;
+  bool want[NKA_MAX_RANKS];
+  for (int r = 0; r < NKA_MAX_RANKS; ++r) want[r] = true;
+  st->peer_n = R;
+  if (!nka_ipc_exchange(c, st->stream, st->peer_box, st->peer_mapped, want)) {
+    st->peer_mapped[me] = nullptr;
+    peer_teardown(st);
+    return false;
+  }
   NkaPeerCtx ctx;
   memset(&ctx, 0, sizeof ctx);
   ctx.nranks = R; ctx.rank = me; ctx.epoch = 0; ctx.timed_out = 0;
   double timeout_s = 120.0;                       // NKA_PEER_TIMEOUT_S: how long to wait for a peer before trapping
   if (const char* e = getenv("NKA_PEER_TIMEOUT_S")) if (atof(e) > 0.0) timeout_s = atof(e);
   ctx.timeout_ns = (unsigned long long)(timeout_s * 1e9);
-  st->peer_n = R;
-  if (ok) {
-    for (int r = 0; r < R; ++r) {
-      if (r == me) { ctx.box[r] = st->peer_box; continue; }
-      void* p = nullptr;
-      if (cudaIpcOpenMemHandle(&p, cards[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-        cudaGetLastError();
-        ok = 0;
-        break;
-      }
-      st->peer_mapped[r] = p;
-      ctx.box[r] = p;
-    }
-  }
-  CUDA_CHECK(cudaMemcpyAsync(d_flag, &ok, sizeof ok, cudaMemcpyHostToDevice, st->stream));
-  rc = g_nccl.AllReduce(d_flag, d_flag, 1, kNcclInt32, kNcclMin, c->comm, st->stream);
-  if (rc != 0) nka_fail(__FILE__, __LINE__, "ncclAllReduce (peer box agreement) failed");
-  CUDA_CHECK(cudaMemcpyAsync(&ok, d_flag, sizeof ok, cudaMemcpyDeviceToHost, st->stream));
-  CUDA_CHECK(cudaStreamSynchronize(st->stream));
-  cudaFree(d_cards);
-  cudaFree(d_flag);
-  if (!ok) { peer_teardown(st); return false; }
+  for (int r = 0; r < R; ++r) ctx.box[r] = st->peer_mapped[r];
+  st->peer_mapped[me] = nullptr;                  // own box: freed, not unmapped
   CUDA_CHECK(cudaMalloc(&st->peer, sizeof(NkaPeerCtx)));
   CUDA_CHECK(cudaMemcpyAsync(st->peer, &ctx, sizeof ctx, cudaMemcpyHostToDevice, st->stream));
   CUDA_CHECK(cudaStreamSynchronize(st->stream));

@@ -28,6 +28,7 @@
 #include "../../include/nka_b200.h"
 #include "../../include/nka_example.h"
 #include "nka_internal.h"
+#include "nka_state.h"      // NKA_MAX_RANKS
 
 #if defined(__CUDACC__)
 #define EX_HD __host__ __device__ __forceinline__
@@ -76,6 +77,9 @@ struct ResParams {
   double* partials;      // one per block
   unsigned* ticket;
   double* sumsq;         // result
+  // row slabs (multi-GPU): u (already u - z) of the row below the slab's first row / above its last
+  // row, received from the neighbouring ranks; nullptr at a physical boundary (u = 0 there)
+  const double *HLO, *HHI;
 };
 
 __device__ __forceinline__ double ex_warp_sum(double v)
@@ -97,7 +101,8 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
     const int j = jmin + p, k = t - j;
     const long long c = wf_base(t, nx, ny) + j;
     const long long bm = wf_base(t - 1, nx, ny), bp = wf_base(t + 1, nx, ny);
-    const bool hl = j > 0, hr = j + 1 < nx, hd = k > 0, hu = k + 1 < ny;
+    const bool bot = k == 0, top = k + 1 >= ny;
+    const bool hl = j > 0, hr = j + 1 < nx, hd = !bot || P.HLO, hu = !top || P.HHI;
     const double* __restrict__ U = P.U;
     const double* __restrict__ Zc = P.Zc;
     auto val = [&](long long i) {
@@ -105,8 +110,8 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
       return Zc ? __dsub_rn(u, __ldg(Zc + i)) : u;                 // u = u - r : F08 :248
     };
     const double uc = val(c);
-    const double ul = hl ? val(bm + j - 1) : 0.0, ud = hd ? val(bm + j) : 0.0;
-    const double ur = hr ? val(bp + j + 1) : 0.0, uu = hu ? val(bp + j) : 0.0;
+    const double ul = hl ? val(bm + j - 1) : 0.0, ud = !bot ? val(bm + j) : (P.HLO ? __ldg(P.HLO + j) : 0.0);
+    const double ur = hr ? val(bp + j + 1) : 0.0, uu = !top ? val(bp + j) : (P.HHI ? __ldg(P.HHI + j) : 0.0);
     // update_system (:122-145): t = 1/(a+u); each face sums the t*h^2 of its (one or two) cells
     // in cell order (left/lower cell first), then ax = 2/ax.
     const double tc = __ddiv_rn(1.0, __dadd_rn(P.a, uc));
@@ -129,7 +134,7 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
     P.R[c] = r; P.AXL[c] = axl; P.AYD[c] = ayd; P.AC[c] = ac;
     if (Zc) P.Unew[c] = uc;
     if (!hr) P.AXR[k] = axr;
-    if (!hu) P.AYT[j] = ayu;
+    if (top) P.AYT[j] = ayu;
     rr = r * r;
   }
   // deterministic two-stage sum of r^2: warp tree, fixed-order across warps, one partial per
@@ -164,6 +169,18 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
     for (int w = 0; w < EX_RES_THREADS / 32; ++w) s += red[w];
     *P.sumsq = s;
     *P.ticket = 0u;
+  }
+}
+
+// Row slabs: the slab's first and last rows of u (after u <- u - z, formed exactly as the residual
+// kernel will form it) packed for the neighbouring ranks.
+__global__ void ex_pack_rows_kernel(const double* __restrict__ U, const double* __restrict__ Zc, int nx, int ny,
+                                    double* __restrict__ lo, double* __restrict__ hi)
+{
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nx; j += gridDim.x * blockDim.x) {
+    const long long c0 = wf_base(j, nx, ny) + j, c1 = wf_base(j + ny - 1, nx, ny) + j;
+    lo[j] = Zc ? __dsub_rn(U[c0], Zc[c0]) : U[c0];
+    hi[j] = Zc ? __dsub_rn(U[c1], Zc[c1]) : U[c1];
   }
 }
 
@@ -218,7 +235,39 @@ struct SsorParams {
   double omega, om1;
   int* err;
   unsigned long long* trace;     // debugging aid (nka_system_ssor_trace): [nstrips][4] globaltimer stamps, or nullptr
+  // Row slabs (multi-GPU): the sweep continues from the rank below (forward) / above (backward).
+  // Edge rows travel as tagged 16-byte slots {lo32, tag, hi32, tag} written straight into the
+  // neighbour's memory over NVLink (tag = sweep number: no flags to reset, no fences).
+  const uint4* halo_lo;          // [nx] local: z of the row below this slab (written by the rank below), or nullptr
+  const uint4* halo_hi;          // [nx] local: z of the row above this slab (written by the rank above), or nullptr
+  uint4* peer_up_lo;             // the upper rank's halo_lo (forward: this slab's top row goes there), or nullptr
+  uint4* peer_dn_hi;             // the lower rank's halo_hi (backward: this slab's bottom row goes there), or nullptr
+  unsigned tag_cur, tag_prev;    // this sweep's number; the previous sweep's (whose edge row holds the "old" values)
+  long long spin_limit;          // cycles a wait may take before it becomes an error (longer across GPUs)
 };
+
+__device__ __forceinline__ double tagged_wait(const uint4* slot, unsigned tag, int* err, long long limit)
+{
+  unsigned lo, t0, hi, t1;
+  const long long c0 = clock64();
+  for (unsigned it = 0;; ++it) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(lo), "=r"(t0), "=r"(hi), "=r"(t1) : "l"(slot) : "memory");
+    if (t0 == tag && t1 == tag) break;
+    if ((it & 255u) == 255u) {
+      if (*(volatile int*)err) return 0.0;
+      if (clock64() - c0 > limit) { *(volatile int*)err = 2; return 0.0; }
+    }
+  }
+  return __hiloint2double((int)hi, (int)lo);
+}
+
+__device__ __forceinline__ void tagged_send(uint4* slot, double v, unsigned tag)
+{
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};"
+               :: "l"(slot), "r"((unsigned)__double2loint(v)), "r"(tag), "r"((unsigned)__double2hiint(v)), "r"(tag)
+               : "memory");
+}
 
 // Raw operands of cell (j, tt - j): own r, ac, left/lower face, own old z; the right face (the left
 // face of cell (j+1,k), or the boundary face); the old z of the downstream horizontal neighbour.
@@ -231,8 +280,12 @@ struct SsorEnt { double r, ac, axl, ayd, zo, zs, axr; };
 struct SsorCooked { double a, b, p0, p1, po, ayd, ac; };
 
 template <int DIR>
-__device__ __forceinline__ SsorCooked ssor_cook(const SsorEnt& cur, const SsorEnt& nxt, bool top, double ayt, double om1)
+__device__ __forceinline__ SsorCooked ssor_cook(const SsorEnt& cur, const SsorEnt& nxt, bool edge, double ayt, double om1,
+                                                double zold_edge)
 {
+  // edge: the cell's next row in travel direction lies outside this slab (forward: above the top
+  // row; backward: below the bottom row).  Its old z is zold_edge: 0 at a physical boundary, the
+  // neighbouring rank's edge row otherwise.
   SsorCooked c;
   c.po = __dmul_rn(om1, cur.zo);
   c.ayd = cur.ayd;
@@ -241,11 +294,11 @@ __device__ __forceinline__ SsorCooked ssor_cook(const SsorEnt& cur, const SsorEn
     c.a = cur.r;
     c.b = cur.axl;
     c.p0 = __dmul_rn(cur.axr, cur.zs);
-    c.p1 = __dmul_rn(top ? ayt : nxt.ayd, nxt.zo);          // nxt = (j, k+1); beyond the top: ayt * 0
+    c.p1 = __dmul_rn(edge ? ayt : nxt.ayd, edge ? zold_edge : nxt.zo);   // nxt = (j, k+1); beyond the top: ayt * edge z
   } else {
     c.a = __dadd_rn(cur.r, __dmul_rn(cur.axl, cur.zs));
     c.b = cur.axr;
-    c.p0 = __dmul_rn(cur.ayd, nxt.zo);                       // nxt = (j, k-1); below the bottom: ayd * 0
+    c.p0 = __dmul_rn(cur.ayd, edge ? zold_edge : nxt.zo);    // nxt = (j, k-1); below the bottom: ayd * edge z
     c.p1 = 0.0;
   }
   return c;
@@ -361,7 +414,7 @@ __device__ __forceinline__ void ssor_receiver(const SsorParams& P, unsigned long
       }
       if ((++it & 255u) == 0u) {
         if (*(volatile int*)P.err) return;
-        if (clock64() - t0 > EX_SPIN_LIMIT) { *(volatile int*)P.err = 1; return; }
+        if (clock64() - t0 > P.spin_limit) { *(volatile int*)P.err = 1; return; }
       }
     }
   }
@@ -414,14 +467,27 @@ __device__ __forceinline__ void ssor_strip(const SsorParams& P, double* ring_ptr
   if (P.trace && lane == 0) P.trace[strip * 4 + 0] = ex_globaltimer();
   for (int i = 0; i < DIST; ++i) issue_next();      // steps 0 .. DIST-1 in flight
 
+  // row slabs: the edge rows of the neighbouring ranks (new: where this sweep comes from; old: where it goes)
+  double znew0 = 0.0, zold_edge = 0.0;
+  if (jvalid) {
+    const uint4* from = DIR > 0 ? P.halo_lo : P.halo_hi;
+    const uint4* beyond = DIR > 0 ? P.halo_hi : P.halo_lo;
+    if (from) znew0 = tagged_wait(from + j, P.tag_cur, P.err, P.spin_limit);
+    if (beyond && !P.zero_old) zold_edge = tagged_wait(beyond + j, P.tag_prev, P.err, P.spin_limit);
+  }
+  uint4* const send_to = DIR > 0 ? P.peer_up_lo : P.peer_dn_hi;
+
   asm volatile("cp.async.wait_group %0;" :: "n"(DIST - 2) : "memory");          // steps 0 and 1 have landed
   SsorEnt e1 = ssor_fetch(ring_ptr, 1, lane);
   SsorCooked ck;
   {
     const SsorEnt e0 = ssor_fetch(ring_ptr, 0, lane);
-    ck = ssor_cook<DIR>(e0, e1, (t_first - j) + 1 >= ny, ayt, P.om1);
+    const int kf = t_first - j;
+    ck = ssor_cook<DIR>(e0, e1, DIR > 0 ? kf + 1 >= ny : kf <= 0, ayt, P.om1, zold_edge);
   }
-  double znew = 0.0;        // own result of the previous step = z(j, k-DIR), new
+  // own result of the previous step = z(j, k-DIR), new; before the first row: the row the
+  // neighbouring rank has just computed, or the boundary value 0
+  double znew = znew0;
   double ayd_prev = 0.0;    // backward: lower face of the previous step's cell = upper face of this one
   long long b_cur = b_first;   // wf_base of the current step's diagonal (for the store)
   int fstage = 2;           // ring stage of step s + 2
@@ -465,6 +531,7 @@ __device__ __forceinline__ void ssor_strip(const SsorParams& P, double* ring_ptr
         ayd_prev = ck.ayd;
         P.Z[b_cur + j] = zc;
         if (is_prod) ch_st(cout + k, (unsigned long long)__double_as_longlong(zc));
+        if (send_to && k == (DIR > 0 ? ny - 1 : 0)) tagged_send(send_to + j, zc, P.tag_cur);   // hand over to the next rank
       }
       if (P.trace && strip == P.nstrips / 2 && lane == 0 && sb + u < 256) P.trace[P.nstrips * 4 + sb + u] = ex_globaltimer();
       b_cur += DIR > 0 ? wf_step(t, nx, ny) : -wf_step(t - 1, nx, ny);
@@ -474,7 +541,7 @@ __device__ __forceinline__ void ssor_strip(const SsorParams& P, double* ring_ptr
       asm volatile("cp.async.wait_group %0;" :: "n"(DIST - 2) : "memory");
       const SsorEnt e2 = ssor_fetch(ring_ptr, fstage, lane);
       fstage = fstage + 1 == STAGES ? 0 : fstage + 1;
-      ck = ssor_cook<DIR>(e1, e2, (k + DIR) + 1 >= ny, ayt, P.om1);
+      ck = ssor_cook<DIR>(e1, e2, DIR > 0 ? (k + DIR) + 1 >= ny : (k + DIR) <= 0, ayt, P.om1, zold_edge);
       e1 = e2;
     }
   }
@@ -521,6 +588,15 @@ struct nka_system {
   double *R = nullptr, *Z = nullptr, *AXL = nullptr, *AYD = nullptr, *AC = nullptr, *AXR = nullptr, *AYT = nullptr;
   unsigned long long* bnd = nullptr;
   unsigned long long* trace = nullptr;   // debugging aid, see nka_system_ssor_trace
+  // row slabs (multi-GPU): this system holds rows [k0, k0 + ny) of an nx x ny_global grid
+  int ny_global = 0, k0 = 0;
+  bool has_lower = false, has_upper = false;
+  NkaComm* comm = nullptr;
+  double *halo_u_lo = nullptr, *halo_u_hi = nullptr;    // [nx] the neighbours' edge rows of u (received before each residual)
+  double *send_lo = nullptr, *send_hi = nullptr;        // [nx] own edge rows of u, packed
+  void* zbox = nullptr;                                 // IPC-exported: uint4 halo_lo[nx], halo_hi[nx] (tagged z rows)
+  void* zbox_mapped[NKA_MAX_RANKS] = {};                // the neighbours' boxes as mapped here
+  unsigned sweep_id = 0;
   int nstrips = 0;
   double* partials = nullptr;
   unsigned* ticket = nullptr;
@@ -570,10 +646,17 @@ struct ExScope {
 
 extern "C" NKASYS nka_system_init(int nx, int ny, double a, int scaling, int device, void* stream)
 {
+  return nka_system_init_slab(nx, ny, 0, ny, a, scaling, device, stream);
+}
+
+extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, double a, int scaling, int device, void* stream)
+{
+  NKA_REQUIRE(k0 >= 0 && k1 <= ny_global && k1 - k0 >= 3, "nka_system_init_slab: a slab needs at least 3 of the grid's rows");
+  const int ny = k1 - k0;
   // preconditions: src-F08/nka_example.F90:90-92
   NKA_REQUIRE(a > 0.0, "nka_system_init: a must be > 0");
-  NKA_REQUIRE(nx >= 3 && ny >= 3, "nka_system_init: nx, ny must be >= 3");
-  NKA_REQUIRE(nx <= (1 << 20) && ny <= (1 << 20), "nka_system_init: grid too large");
+  NKA_REQUIRE(nx >= 3 && ny_global >= 3, "nka_system_init: nx, ny must be >= 3");
+  NKA_REQUIRE(nx <= (1 << 20) && ny_global <= (1 << 20), "nka_system_init: grid too large");
   NKA_REQUIRE(scaling == 0 || scaling == 1, "nka_system_init: scaling must be 0 (F95/C) or 1 (F08)");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -587,7 +670,8 @@ extern "C" NKASYS nka_system_init(int nx, int ny, double a, int scaling, int dev
   sy->stream = (cudaStream_t)stream;
   sy->nx = nx; sy->ny = ny; sy->a = a; sy->scaling = scaling;
   sy->n = (size_t)nx * ny;
-  sy->hx = 1.0 / nx; sy->hy = 1.0 / ny;
+  sy->ny_global = ny_global; sy->k0 = k0;
+  sy->hx = 1.0 / nx; sy->hy = 1.0 / ny_global;
   if (scaling == 0) { sy->fx = sy->hx / sy->hy; sy->fy = sy->hy / sy->hx; sy->q = sy->hx * sy->hy; }   // src-C/nka_example.c:97,225-226
   else { sy->fx = sy->hx * sy->hx; sy->fy = sy->hy * sy->hy; sy->q = 1.0; }                           // F08 :100,:132-135
   const size_t bytes = sy->n * sizeof(double);
@@ -628,9 +712,57 @@ extern "C" void nka_system_delete(NKASYS sy)
   cudaFree(sy->U[0]); cudaFree(sy->U[1]); cudaFree(sy->R); cudaFree(sy->Z); cudaFree(sy->AXL);
   cudaFree(sy->AYD); cudaFree(sy->AC); cudaFree(sy->AXR); cudaFree(sy->AYT); cudaFree(sy->bnd);
   cudaFree(sy->trace);
+  if (sy->comm) { nka_ipc_unmap(sy->comm, sy->zbox_mapped); nka_comm_release(sy->comm); }
+  cudaFree(sy->zbox); cudaFree(sy->halo_u_lo); cudaFree(sy->halo_u_hi); cudaFree(sy->send_lo); cudaFree(sy->send_hi);
   cudaFree(sy->partials); cudaFree(sy->ticket); cudaFree(sy->result); cudaFree(sy->stage);
   cudaFreeHost(sy->result_host);
   delete sy;
+}
+
+// Collective.  Rank r must hold the slab directly above rank r-1's.  Creates the communicator
+// (shared later with the accelerator: nka_comm_share_system), the receive buffers for the edge rows
+// of u, and the tagged edge rows of z that the neighbouring ranks write through NVLink (CUDA IPC).
+extern "C" int nka_system_comm_init(NKASYS sy, int nranks, int rank, const void* id128)
+{
+  NKA_REQUIRE(sy != NULL && id128 != NULL, "nka_system_comm_init: null argument");
+  NKA_REQUIRE(nranks >= 1 && nranks <= NKA_MAX_RANKS && rank >= 0 && rank < nranks, "nka_system_comm_init: bad rank/nranks");
+  NKA_REQUIRE(sy->comm == nullptr, "nka_system_comm_init: already attached");
+  NKA_REQUIRE((rank == 0) == (sy->k0 == 0) && (rank == nranks - 1) == (sy->k0 + sy->ny == sy->ny_global),
+              "nka_system_comm_init: slabs must be stacked in rank order");
+  if (!nka_nccl_load() || !g_nccl.Send || !g_nccl.Recv || !g_nccl.GroupStart || !g_nccl.GroupEnd) return -1;
+  DeviceGuard guard(sy->device);
+  NkaId128 id;
+  memcpy(id.bytes, id128, sizeof id.bytes);
+  void* comm = nullptr;
+  const int rc = g_nccl.CommInitRank(&comm, nranks, id, rank);
+  if (rc != 0) return rc;
+  NkaComm* c = new NkaComm();
+  c->comm = comm; c->owned = true; c->nranks = nranks; c->rank = rank;
+  sy->comm = c;
+  sy->has_lower = rank > 0;
+  sy->has_upper = rank + 1 < nranks;
+  const size_t row = (size_t)sy->nx * sizeof(double);
+  CUDA_CHECK(cudaMalloc(&sy->halo_u_lo, row)); CUDA_CHECK(cudaMalloc(&sy->halo_u_hi, row));
+  CUDA_CHECK(cudaMalloc(&sy->send_lo, row)); CUDA_CHECK(cudaMalloc(&sy->send_hi, row));
+  size_t zbytes = 2 * (size_t)sy->nx * sizeof(uint4);
+  zbytes = (zbytes + (2u << 20) - 1) / (2u << 20) * (2u << 20);          // whole 2 MiB granules: what CUDA IPC exports
+  CUDA_CHECK(cudaMalloc(&sy->zbox, zbytes));
+  CUDA_CHECK(cudaMemsetAsync(sy->zbox, 0, zbytes, sy->stream));          // tag 0 = never written (sweeps count from 1)
+  CUDA_CHECK(cudaStreamSynchronize(sy->stream));
+  bool want[NKA_MAX_RANKS];
+  for (int r = 0; r < NKA_MAX_RANKS; ++r) want[r] = (r == rank - 1 || r == rank + 1);
+  if (!nka_ipc_exchange(c, sy->stream, sy->zbox, sy->zbox_mapped, want))
+    nka_fail(__FILE__, __LINE__, "nka_system_comm_init: the ranks cannot map each other's memory (CUDA IPC / NVLink peer "
+                                 "access): the slab-pipelined SSOR sweep needs it");
+  sy->zbox_mapped[rank] = nullptr;
+  return 0;
+}
+
+// The accelerator of a slab system sums its dot products over the same ranks.
+extern "C" void nka_comm_share_system(NKA acc, NKASYS sy)
+{
+  NKA_REQUIRE(acc != NULL && sy != NULL && sy->comm != NULL, "nka_comm_share_system: the system has no communicator");
+  nka_attach_shared_comm(acc, sy->comm);
 }
 
 extern "C" size_t nka_system_size(NKASYS sy) { NKA_REQUIRE(sy != NULL, "nka_system_size: null handle"); return sy->n; }
@@ -700,6 +832,26 @@ extern "C" double nka_system_residual(NKASYS sy, int subtract_z)
   P.R = sy->R; P.AXL = sy->AXL; P.AYD = sy->AYD; P.AC = sy->AC; P.AXR = sy->AXR; P.AYT = sy->AYT;
   P.a = sy->a; P.fx = sy->fx; P.fy = sy->fy; P.q = sy->q;
   P.partials = sy->partials; P.ticket = sy->ticket; P.sumsq = sy->result;
+  P.HLO = sy->has_lower ? sy->halo_u_lo : nullptr;
+  P.HHI = sy->has_upper ? sy->halo_u_hi : nullptr;
+  if (sy->comm && sy->comm->nranks > 1) {
+    // edge rows of (u - z) to and from the neighbouring slabs: 2 x nx doubles each way
+    ex_pack_rows_kernel<<<ex_grid(sy, sy->nx, 256), 256, 0, sy->stream>>>(P.U, P.Zc, sy->nx, sy->ny, sy->send_lo, sy->send_hi);
+    CUDA_CHECK(cudaGetLastError());
+    sy->launches += 1;
+    const int me = sy->comm->rank;
+    int rc = g_nccl.GroupStart();
+    if (sy->has_lower) {
+      rc |= g_nccl.Send(sy->send_lo, sy->nx, kNcclFloat64, me - 1, sy->comm->comm, sy->stream);
+      rc |= g_nccl.Recv(sy->halo_u_lo, sy->nx, kNcclFloat64, me - 1, sy->comm->comm, sy->stream);
+    }
+    if (sy->has_upper) {
+      rc |= g_nccl.Send(sy->send_hi, sy->nx, kNcclFloat64, me + 1, sy->comm->comm, sy->stream);
+      rc |= g_nccl.Recv(sy->halo_u_hi, sy->nx, kNcclFloat64, me + 1, sy->comm->comm, sy->stream);
+    }
+    rc |= g_nccl.GroupEnd();
+    if (rc != 0) nka_fail(__FILE__, __LINE__, "nka_system_residual: NCCL edge-row exchange failed");
+  }
   const int maxlen = sy->nx < sy->ny ? sy->nx : sy->ny;
   dim3 grid(sy->nx + sy->ny - 1, (maxlen + EX_RES_THREADS - 1) / EX_RES_THREADS);
   {
@@ -709,6 +861,11 @@ extern "C" double nka_system_residual(NKASYS sy, int subtract_z)
     sy->launches += 1;
   }
   if (subtract_z) sy->cur ^= 1;
+  if (sy->comm && sy->comm->nranks > 1) {
+    // global norm: sum of the slabs' sums of squares, the same bits on every rank
+    const int rc = g_nccl.AllReduce(sy->result, sy->result, 1, kNcclFloat64, kNcclSum, sy->comm->comm, sy->stream);
+    if (rc != 0) nka_fail(__FILE__, __LINE__, "nka_system_residual: ncclAllReduce failed");
+  }
   CUDA_CHECK(cudaMemcpyAsync(sy->result_host, sy->result, 2 * sizeof(double), cudaMemcpyDeviceToHost, sy->stream));
   CUDA_CHECK(cudaStreamSynchronize(sy->stream));
   int errw = 0;
@@ -738,12 +895,22 @@ extern "C" int nka_system_pc_ssor(NKASYS sy, int nsweep, double omega)
   P.omega = omega; P.om1 = 1.0 - omega;
   P.err = reinterpret_cast<int*>(sy->result + 1);
   P.trace = sy->trace;
+  const bool slabs = sy->comm && sy->comm->nranks > 1;
+  uint4* zb = reinterpret_cast<uint4*>(sy->zbox);
+  P.halo_lo = sy->has_lower ? zb : nullptr;
+  P.halo_hi = sy->has_upper ? zb + sy->nx : nullptr;
+  // the upper rank's halo_lo is the first row of its box, the lower rank's halo_hi the second row of its box
+  P.peer_up_lo = sy->has_upper ? reinterpret_cast<uint4*>(sy->zbox_mapped[sy->comm->rank + 1]) : nullptr;
+  P.peer_dn_hi = sy->has_lower ? reinterpret_cast<uint4*>(sy->zbox_mapped[sy->comm->rank - 1]) + sy->nx : nullptr;
+  P.spin_limit = slabs ? 60 * EX_SPIN_LIMIT : EX_SPIN_LIMIT;          // ~2 s on one GPU, ~2 min when another GPU is upstream
   ExScope t(sy, 0);
   for (int i = 0; i < nsweep; ++i) {
     P.zero_old = (i == 0) ? 1 : 0;                       // z = 0 start (:158): nothing to read yet
+    P.tag_prev = sy->sweep_id; P.tag_cur = ++sy->sweep_id;
     ex_ssor_sweep<1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     P.zero_old = 0;
+    P.tag_prev = sy->sweep_id; P.tag_cur = ++sy->sweep_id;
     ex_ssor_sweep<-1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     sy->launches += 2;

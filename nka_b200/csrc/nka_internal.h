@@ -29,6 +29,10 @@ struct NkaNcclApi {
   int (*CommInitRank)(void**, int, NkaId128, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -48,5 +52,16 @@ struct NkaComm {
   int nranks = 1, rank = 0;
   int refs = 1;
 };
+struct nka_state;
+// an accelerator joins an existing communicator (a vector's, a slab system's): nka_capi.cu
+void nka_attach_shared_comm(nka_state* st, NkaComm* c);
 NkaComm* nka_comm_retain(NkaComm* c);
 void nka_comm_release(NkaComm* c);
+
+// Collective over the communicator: every rank offers one device allocation (cudaMalloc'ed, a
+// multiple of 2 MiB of its own) and receives, in mapped[r] for each r with want[r], rank r's
+// allocation mapped into this process (CUDA IPC; mapped[rank] = local).  The outcome is
+// unanimous: returns false on EVERY rank (nothing left mapped) if any rank could not export or
+// open what it wanted.  Unmap with nka_ipc_unmap.
+bool nka_ipc_exchange(NkaComm* c, cudaStream_t stream, void* local, void** mapped, const bool* want);
+void nka_ipc_unmap(NkaComm* c, void** mapped);

@@ -22,25 +22,43 @@ class System:
     """type(system): the discrete nonlinear system -div((a+u) grad u) = q, device resident."""
 
     def __init__(self, a: float | None = None, nx: int | None = None, ny: int | None = None,
-                 scaling: int = 1, device: int = -1, stream: int | None = None):
+                 scaling: int = 1, device: int = -1, stream: int | None = None,
+                 slab: tuple[int, int] | None = None):
         self._h = None
         self._lib = _lib.load()
+        self.distributed = False
         if a is not None:
-            self.init(a, nx, ny, scaling=scaling, device=device, stream=stream)
+            self.init(a, nx, ny, scaling=scaling, device=device, stream=stream, slab=slab)
 
-    def init(self, a: float, nx: int, ny: int, scaling: int = 1, device: int = -1, stream: int | None = None):
+    def init(self, a: float, nx: int, ny: int, scaling: int = 1, device: int = -1, stream: int | None = None,
+             slab: tuple[int, int] | None = None):
         """init(a, nx, ny): src-F08/nka_example.F90:86-101.  scaling=0 gives the F95/C flavour
-        (q = hx*hy), scaling=1 the F08 flavours (q = 1)."""
+        (q = hx*hy), scaling=1 the F08 flavours (q = 1).  slab=(k0, k1): this process holds rows
+        [k0, k1) of the nx x ny grid (one process per GPU; call comm_init next); self.ny is then
+        the LOCAL number of rows, self.ny_global the grid's."""
         if not a > 0.0:
             raise ValueError("a must be > 0")          # ASSERT(a > 0) :90
         if nx < 3 or ny < 3:
             raise ValueError("nx, ny must be >= 3")    # :91-92
         self.delete()
-        self._h = self._lib.nka_system_init(nx, ny, a, scaling, device, stream)
-        self.nx, self.ny, self.a, self.scaling = nx, ny, a, scaling
+        k0, k1 = slab if slab is not None else (0, ny)
+        if not (0 <= k0 and k1 <= ny and k1 - k0 >= 3):
+            raise ValueError("a slab needs at least 3 rows of the grid")
+        self._h = self._lib.nka_system_init_slab(nx, ny, k0, k1, a, scaling, device, stream)
+        self.nx, self.ny, self.a, self.scaling = nx, k1 - k0, a, scaling
+        self.ny_global, self.k0, self.k1 = ny, k0, k1
         self.stream = stream
         self.device = device
+        self.distributed = False
         return self
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        """Collective: join the slabs (rank r directly above rank r-1) into one grid."""
+        buf = C.create_string_buffer(unique_id, 128)
+        rc = self._lib.nka_system_comm_init(self._handle(), nranks, rank, buf)
+        if rc != 0:
+            raise RuntimeError("nka_system_comm_init failed (%d)" % rc)
+        self.distributed = nranks > 1
 
     def delete(self):
         if self._h:
@@ -113,6 +131,8 @@ class Solver:
         if self.accel is not None:
             self.accel.delete()
         self.accel = NKA(sys.size(), mvec, vtol, device=sys.device, stream=sys.stream) if mvec > 0 else None
+        if self.accel is not None and sys.distributed:
+            _lib.load().nka_comm_share_system(self.accel._handle(), sys._handle())   # dot products over all slabs
         return self
 
     def solve(self, maxitr: int | None = None, tol: float | None = None, record_nvec: bool = False) -> dict:
@@ -135,3 +155,21 @@ class Solver:
         if self.accel is not None:
             self.accel.delete()
             self.accel = None
+
+
+def row_slab(ny: int, world: int, rank: int) -> tuple[int, int]:
+    """Balanced contiguous rows [k0, k1) of rank `rank`."""
+    return (ny * rank) // world, (ny * (rank + 1)) // world
+
+
+def distributed_system(a: float, nx: int, ny: int, scaling: int = 1, group=None, device: int = -1,
+                       stream: int | None = None) -> System:
+    """Collective (torch.distributed is only the plumbing that ships the NCCL id): every rank gets
+    its row slab of the nx x ny grid, joined for halo rows, the global norm and the slab-pipelined
+    SSOR sweep."""
+    import torch.distributed as dist
+    from .distributed import exchange_unique_id
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sy = System(a, nx, ny, scaling=scaling, device=device, stream=stream, slab=row_slab(ny, world, rank))
+    sy.comm_init(world, rank, exchange_unique_id(group))
+    return sy

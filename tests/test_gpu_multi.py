@@ -94,3 +94,107 @@ def test_two_gpu_slabs_match_serial_oracle(name, mode):
     for t in range(len(inputs)):
         joined = np.concatenate([got[0]["outs"][t], got[1]["outs"][t]])
         assert np.linalg.norm(joined - arbiter[t]) / scales[t] <= tols[t], (name, t)
+
+
+# ---------------------------------------------------------------------------------------------
+# the example on row slabs (BASELINE.json configs[3] in miniature): halo rows for the residual,
+# global norm, slab-pipelined exact-order SSOR, accelerator over all slabs
+# ---------------------------------------------------------------------------------------------
+def _example_worker(rank, world, port, case, q):
+    os.environ["NKA_PEER_TIMEOUT_S"] = "30"
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    from nka_b200.example import distributed_system, Solver, FIELD_U, FIELD_R, FIELD_Z
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        out = {}
+        if case["kind"] == "kernels":
+            nx, ny = case["nx"], case["ny"]
+            sy = distributed_system(0.02, nx, ny, scaling=1, device=rank)
+            rng = np.random.default_rng(42)
+            u = rng.uniform(0.0, 0.3, (ny, nx))
+            z = rng.uniform(-0.01, 0.01, (ny, nx))
+            sy.set(FIELD_U, u[sy.k0:sy.k1])
+            sy.set(FIELD_Z, z[sy.k0:sy.k1])
+            out["rnorm"] = sy.residual(subtract_z=True)
+            out["u"] = sy.get(FIELD_U)
+            out["r"] = sy.get(FIELD_R)
+            sy.pc_ssor(case["nsweep"], 1.4)
+            out["z"] = sy.get(FIELD_Z)
+            sy.pc_ssor(1, 1.4)                      # a second application: tags keep counting
+            out["z2"] = sy.get(FIELD_Z)
+            out["rows"] = (sy.k0, sy.k1)
+            sy.delete()
+        else:
+            sy = distributed_system(0.02, case["nx"], case["ny"], scaling=case["scaling"], device=rank)
+            so = Solver(sy, nsweep=2, omega=1.4, mvec=case["mvec"], vtol=0.01)
+            res = so.solve(maxitr=case.get("maxitr"), record_nvec=case["mvec"] > 0)
+            out = {"iters": res["iters"], "rnorm": res["rnorm"], "nvec": res.get("nvec"),
+                   "mode": so.accel.comm_mode() if so.accel else None}
+            so.delete(); sy.delete()
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run_example(case, world=2):
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_example_worker, args=(r, world, port, case, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return got
+
+
+@pytest.mark.parametrize("nx,ny,nsweep", [(70, 64, 2), (33, 9, 1), (200, 131, 3)])
+def test_slab_residual_and_ssor_bit_identical_to_serial_loops(nx, ny, nsweep):
+    """Two row slabs: u - z, residual and the SSOR sweeps equal the CPU loops on the whole grid bit
+    for bit (the sweep crosses the slab boundary strip by strip through NVLink peer memory)."""
+    from oracle import api
+    got = _run_example({"kind": "kernels", "nx": nx, "ny": ny, "nsweep": nsweep})
+    rng = np.random.default_rng(42)
+    u = rng.uniform(0.0, 0.3, (ny, nx))
+    z = rng.uniform(-0.01, 0.01, (ny, nx))
+    orc = api.OracleSystem(nx, ny, 0.02, 1)
+    unew = u - z
+    pad = np.zeros((ny + 2, nx + 2)); pad[1:-1, 1:-1] = unew
+    r = orc.residual(pad).reshape(ny, nx)
+    zz = orc.pc_ssor(nsweep, 1.4, r.ravel().copy()).reshape(ny, nx)
+    zz2 = orc.pc_ssor(1, 1.4, r.ravel().copy()).reshape(ny, nx)
+    assert got[0]["rows"][1] == got[1]["rows"][0]
+    for key, want in (("u", unew), ("r", r), ("z", zz), ("z2", zz2)):
+        joined = np.concatenate([got[0][key], got[1][key]], axis=0)
+        assert np.array_equal(joined, want), key
+    assert got[0]["rnorm"] == got[1]["rnorm"]
+    assert abs(got[0]["rnorm"] - orc.norm2(r.ravel())) <= 1e-13 * got[0]["rnorm"]
+
+
+def test_slab_example_reproduces_golden_tables():
+    """The reference's pinned run (src-F95/reference_output) on two GPUs: 26 accelerated iterations,
+    every printed line equal; 367 unaccelerated."""
+    from oracle import api
+    with open(os.path.join(ROOT, "tests", "golden", "example_c_f95.txt")) as fh:
+        acc_txt, unacc_txt = fh.read().split("UNACCELERATED SOLVE")
+    lines = lambda text: [ln for ln in text.splitlines() if ":" in ln[:4] and ln[:3].strip().isdigit()]
+    got = _run_example({"kind": "solve", "nx": 50, "ny": 50, "scaling": 0, "mvec": 5})
+    assert got[0]["iters"] == got[1]["iters"] == 26
+    assert got[0]["mode"] == "peer"
+    assert np.array_equal(got[0]["rnorm"], got[1]["rnorm"])
+    assert api.format_table(got[0]["rnorm"]) == lines(acc_txt)
+    assert list(got[0]["nvec"]) == [0, 1, 2, 3, 4, 5] + [5] * 20
+    got = _run_example({"kind": "solve", "nx": 50, "ny": 50, "scaling": 0, "mvec": 0})
+    assert got[0]["iters"] == 367
+    assert api.format_table(got[0]["rnorm"]) == lines(unacc_txt)
