@@ -212,7 +212,7 @@ static int resident_b(NKA st, int nz, int V)
   if (st->occ_b[nz][V] < 0) {
     int nb = 0;
     NKA_REQUIRE(nka_get_pass_b(nz, V) != nullptr, "pass B is not instantiated for this subspace size in this build");
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nka_get_pass_b(nz, V), NKA_THREADS_B, 0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, nka_get_pass_b(nz, V), nka_threads_b(nz), 0));
     st->occ_b[nz][V] = nb > 0 ? nb : 1;
   }
   return st->occ_b[nz][V];
@@ -517,9 +517,9 @@ static void launch_mid(NKA st, const UpdateShape& u, double* f)
 
 static void launch_pass_b(NKA st, const UpdateShape& u, double* f, size_t off, size_t len)
 {
-  const int grid = grid_for(st, per_sm_b(st, u.nz, u.V, len), len, u.V, NKA_THREADS_B);
+  const int grid = grid_for(st, per_sm_b(st, u.nz, u.V, len), len, u.V, nka_threads_b(u.nz));
   SpanScope t(st, T_PASS_B);
-  nka_get_pass_b(u.nz, u.V)<<<grid, NKA_THREADS_B, 0, st->stream>>>(f + off, st->W + off, st->Z + off, st->ld, len, st->S);
+  nka_get_pass_b(u.nz, u.V)<<<grid, nka_threads_b(u.nz), 0, st->stream>>>(f + off, st->W + off, st->Z + off, st->ld, len, st->S);
   CUDA_CHECK(cudaGetLastError());
   st->launches += 1;
 }
@@ -775,8 +775,8 @@ extern "C" void nka_launch_geometry(NKA st, int* grid_a, int* grid_b, int* threa
   const int NC = may_skip ? st->mvec : L;
   if (grid_a) *grid_a = L > 0 ? grid_for(st, per_sm_a(st, NC, 2, st->vlen), st->vlen, 2, NKA_THREADS_A) : 0;
   const int nz = nz_expected(st);
-  if (grid_b) *grid_b = grid_for(st, per_sm_b(st, nz, 2, st->vlen), st->vlen, 2, NKA_THREADS_B);
-  if (threads) *threads = NKA_THREADS_A * 10000 + NKA_THREADS_B;
+  if (grid_b) *grid_b = grid_for(st, per_sm_b(st, nz, 2, st->vlen), st->vlen, 2, nka_threads_b(nz));
+  if (threads) *threads = NKA_THREADS_A * 10000 + nka_threads_b(nz);
 }
 
 extern "C" const char* nka_b200_version(void) { return NKA_VERSION; }

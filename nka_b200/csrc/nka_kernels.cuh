@@ -50,6 +50,13 @@
 #define NKA_LOAD_STREAM 0    // 0: ld.global.nc, 1: ld.global.cs (evict-first), 2/3: L1::no_allocate variants
 #endif
 #define NKA_STATE_THREADS 128
+// Pass B holds NZ column values (double2) and 2 NZ coefficients per thread: beyond 12 columns the
+// 128 registers a 512-thread CTA allows spill (388 B at NZ = 20: 5.9 instead of 7.0 TB/s), so the
+// larger instantiations run 256 threads with up to 255 registers.
+#ifndef NKA_THREADS_B_WIDE_FROM
+#define NKA_THREADS_B_WIDE_FROM 13
+#endif
+__host__ __device__ constexpr int nka_threads_b(int nz) { return nz >= NKA_THREADS_B_WIDE_FROM ? 256 : NKA_THREADS_B; }
 
 // ---------------------------------------------------------------------------
 // 16-byte / 8-byte element access with streaming cache hints.  V = 2 uses
@@ -461,7 +468,7 @@ __device__ __forceinline__ void nka_pass_b_elem(double* __restrict__ f, double* 
 }
 
 template <int NZ, int V>
-__global__ void __launch_bounds__(NKA_THREADS_B, NKA_MINB_B)
+__global__ void __launch_bounds__(nka_threads_b(NZ), NKA_MINB_B)
 nka_pass_b(double* __restrict__ f, double* W, double* Z, size_t ld, size_t n, const NkaDevState* __restrict__ S)
 {
   constexpr int NZA = NZ > 0 ? NZ : 1;
@@ -480,8 +487,8 @@ nka_pass_b(double* __restrict__ f, double* W, double* Z, size_t ld, size_t n, co
     coefY[k] = on ? B->coefY[k] : 0.0;
   }
   const size_t nv = n / V;
-  const size_t stride = (size_t)gridDim.x * NKA_THREADS_B;
-  const size_t start = (size_t)blockIdx.x * NKA_THREADS_B + threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * nka_threads_b(NZ);
+  const size_t start = (size_t)blockIdx.x * nka_threads_b(NZ) + threadIdx.x;
   const bool full = (nz == NZ) && has_pair && write_f && (S->planM.n == 0);
   if (full) {
     for (size_t i = start; i < nv; i += stride)

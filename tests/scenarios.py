@@ -144,6 +144,10 @@ SCENARIOS = {
     "mixed_n257_m5":       (257, 5, 0.1, lambda: mixed_stress(257, 22, 17)),
     "odd_n1023_m7":        (1023, 7, 0.01, lambda: iid(1023, 12, 18)),
     "n4097_m2":            (4097, 2, 0.01, lambda: iid(4097, 8, 19)),
+    # wide subspaces: the 256-thread instantiations of pass B (13 columns and more)
+    "iid_n2000_m16":       (2000, 16, 0.01, lambda: iid(2000, 40, 20)),
+    "collinear_n400_m20":  (400, 20, 0.05, lambda: collinear(400, 48, 21, rho=0.9, eps=2e-1, delta=1e-3)),
+    "iid_n513_m32":        (513, 32, 0.01, lambda: iid(513, 70, 22)),
 }
 
 
