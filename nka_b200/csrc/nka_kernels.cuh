@@ -285,6 +285,16 @@ __device__ __forceinline__ void nka_peer_allreduce(NkaPeerCtx* __restrict__ P, d
 struct NkaStateStage {
   NkaDevState st;
   double dots[2 * NKA_MAXSLOT];
+  NkaStepScratch x;
+};
+
+// The step is run by the 32 lanes of one warp (nka_state.h: lane-parallel over entries, the
+// reference's operation order within each entry).
+struct NkaWarpPar {
+  int l;
+  __device__ __forceinline__ int lane() const { return l; }
+  __device__ __forceinline__ int nlanes() const { return 32; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 
 __device__ __forceinline__ void nka_stage_in(NkaStateStage& sm, const NkaDevState* S, const double* dots)
@@ -307,9 +317,10 @@ __device__ __forceinline__ void nka_stage_out(const NkaStateStage& sm, NkaDevSta
 
 // One copy of the scalar step per translation unit (it is inlined nowhere: pass A is
 // instantiated 66 times and would otherwise carry 66 copies of it).
-static __device__ __noinline__ int nka_state_step_dev(NkaDevState* st, const double* dots, int have_last)
+static __device__ __noinline__ int nka_state_step_dev(NkaDevState* st, NkaStepScratch* x, const double* dots, int have_last)
 {
-  return nka_state_step(*st, dots, NKA_MAXSLOT, have_last);
+  const NkaWarpPar par = {(int)(threadIdx.x & 31)};
+  return nka_state_step(*st, *x, dots, NKA_MAXSLOT, have_last, par);
 }
 
 // Runs the step on the staged copy (dots already in sm.dots) and commits it,
@@ -317,7 +328,10 @@ static __device__ __noinline__ int nka_state_step_dev(NkaDevState* st, const dou
 __device__ __forceinline__ void nka_run_state_step(NkaStateStage& sm, NkaDevState* S, int have_last)
 {
   __shared__ int need_more;
-  if (threadIdx.x == 0) need_more = nka_state_step_dev(&sm.st, sm.dots, have_last);
+  if (threadIdx.x < 32) {                         // warp 0, all lanes
+    const int r = nka_state_step_dev(&sm.st, &sm.x, sm.dots, have_last);
+    if (threadIdx.x == 0) need_more = r;
+  }
   __syncthreads();
   if (need_more) {
     if (threadIdx.x == 0) S->need_fixup = 1;

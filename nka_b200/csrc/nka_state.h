@@ -222,6 +222,51 @@ NKA_HD void nka_state_relax(NkaDevState& S)
   nka_build_plan_a(S);
 }
 
+// How the step is executed: by one thread (the host model in tests/model/) or by the 32 lanes
+// of a warp (the device).  Every entry of the Gram row, of the Cholesky factor and of the two
+// triangular solves is computed with the reference's operations in the reference's order; the
+// lanes only work on DIFFERENT entries at the same time (column-oriented: as soon as a vector is
+// known to stay, every later row forms its entry against it), so results do not depend on the
+// number of lanes.  The decisions (capacity eviction, vtol drop, relax guard) stay sequential.
+struct NkaSerial {
+  NKA_HD int lane() const { return 0; }
+  NKA_HD int nlanes() const { return 1; }
+  NKA_HD void sync() const {}
+};
+
+// Working storage of one step, shared by the lanes.
+struct NkaStepScratch {
+  int ord[NKA_MAXSLOT];          // the list as pass A saw it: slot at each position
+  int removed[NKA_MAXSLOT];      // slot left the list during this call
+  int act[NKA_MAXSLOT];          // the slots known to stay, in list order (p first)
+  int lst[NKA_MAXSLOT];          // the list after the update
+  double rhs[NKA_MAXSLOT];       // <f, w_k>, then the running right-hand side of the solves
+  double hkk[NKA_MAXSLOT];       // 1 - sum of squares of the factor row being formed, per slot
+  int na, nl, nvec, jr, has_pair, ret, stop, newcol, pending_at_entry, nw;
+  double s;
+};
+
+// Row entries against the newly fixed column act[a], for every row at a position >= from that
+// still awaits its decision:   h(k,j) = (G(j,k) - sum_{i before j} h(k,i) h(j,i)) / h(j,j)
+// (src-C/...c:350-360), and the running  hkk -= h(k,j)^2.
+template <class Par>
+NKA_HD void nka_cholesky_column(NkaDevState& S, NkaStepScratch& X, int a, int from, int L, int missing, const Par& par)
+{
+  const int j = X.act[a];
+  const double* hj = &NKA_H(S, j, 0);
+  const double hjj = hj[j];
+  for (int q = from + par.lane(); q < L; q += par.nlanes()) {
+    if (q == missing) continue;
+    const int k = X.ord[q];
+    double* hk = &NKA_H(S, k, 0);
+    double hkj = NKA_H(S, j, k);
+    for (int ii = 0; ii < a; ++ii) hkj -= hk[X.act[ii]] * hj[X.act[ii]];
+    hkj /= hjj;
+    hk[j] = hkj;
+    X.hkk[k] -= hkj * hkj;
+  }
+}
+
 // The scalar part of one accel_update.  `dots` holds what pass A reduced, laid
 // out as dd[j] = d_0 . d_j  (j < ncol)  followed by  fd[j] = f . d_j  at
 // dots[stride + j]; ignored when the list was empty on entry.
@@ -230,174 +275,203 @@ NKA_HD void nka_state_relax(NkaDevState& S)
 // factorisation turns out to need it, nothing is committed and the function
 // returns 1 with need_fixup set; the caller then computes the two missing dot
 // products and calls again with have_last = 1.  Returns 0 when the step is done.
-NKA_HD int nka_state_step(NkaDevState& S, const double* dots, int stride, int have_last)
+// Called by all par.nlanes() lanes together; S and X are shared by them.
+template <class Par>
+NKA_HD int nka_state_step(NkaDevState& S, NkaStepScratch& X, const double* dots, int stride, int have_last, const Par& par)
 {
-  int ord[NKA_MAXSLOT];
-  bool removed[NKA_MAXSLOT];
-  double rhs[NKA_MAXSLOT];
+  const bool lead = par.lane() == 0;
   const int L = S.planA.ncol;
   const int missing = (S.planA.skip_last && !have_last) ? L - 1 : -1;   // position without dots
-  for (int j = 0; j < L; ++j) ord[j] = S.planA.col[j];
-  for (int k = 0; k < NKA_MAXSLOT; ++k) { removed[k] = false; rhs[k] = 0.0; }
   const double* dd = dots;
   const double* fd = dots + stride;
-  const int pending_at_entry = S.pending;
+  par.sync();
+  if (lead) {
+    for (int j = 0; j < L; ++j) X.ord[j] = S.planA.col[j];
+    for (int k = 0; k < NKA_MAXSLOT; ++k) { X.removed[k] = 0; X.rhs[k] = 0.0; X.hkk[k] = 1.0; }
+    X.pending_at_entry = S.pending;
+    X.jr = L;            // first list position whose slot left the list this call
+    X.has_pair = 0;
+    X.ret = 0; X.stop = 0; X.newcol = 0;
+    X.s = 0.0;
+    S.ndrop_last = 0;
+    S.evicted_last = 0;
+    S.relaxed_last = 0;
+    S.min_margin = 1.0e300;
+    S.s_last = 0.0;
+    S.planM.n = 0;
+    S.need_fixup = 0;
 
-  S.ndrop_last = 0;
-  S.evicted_last = 0;
-  S.relaxed_last = 0;
-  S.min_margin = 1.0e300;
-  S.s_last = 0.0;
-  S.planM.n = 0;
-  S.need_fixup = 0;
-  int jr = L;            // first list position whose slot left the list this call
-  int has_pair = 0;
-  double s = 0.0;
-
-  // Step A: norm of the new difference; zero guard.  src-C/...c:295-311
-  if (S.pending) {
-    s = NKA_SQRT(dd[0]);
-    S.s_last = s;
-    if (s == 0.0) {
-      if (missing >= 0) { S.need_fixup = 1; return 1; }   // every old pair stays: its f.d is needed
-      removed[nka_list_relax(S)] = true;
-      S.relaxed_last = 1;
-      jr = 0;
+    // Step A: norm of the new difference; zero guard.  src-C/...c:295-311
+    if (S.pending) {
+      X.s = NKA_SQRT(dd[0]);
+      S.s_last = X.s;
+      if (X.s == 0.0) {
+        if (missing >= 0) { S.need_fixup = 1; X.ret = 1; }   // every old pair stays: its f.d is needed
+        else {
+          X.removed[nka_list_relax(S)] = 1;
+          S.relaxed_last = 1;
+          X.jr = 0;
+        }
+      }
     }
   }
+  par.sync();
+  if (X.ret) return 1;
 
   // Step B: Gram row, refactorisation, drops.  src-C/...c:313-385
   if (S.pending) {
     const int p = S.first;
-    S.s[p] = s;
-    S.chained[p] = 1;
-    has_pair = 1;
+    const double s = X.s;
+    if (lead) {
+      S.s[p] = s;
+      S.chained[p] = 1;
+      X.has_pair = 1;
+      NKA_H(S, p, p) = 1.0;
+      X.nvec = 1;
+      X.na = 1;
+      X.act[0] = p;
+    }
     // <w_1, w_k> = (d_0 . d_k) / (s s_k); the reference normalises first (:317-324)
-    for (int j = 1; j < L; ++j) {
-      const int k = ord[j];
-      if (j != missing) NKA_H(S, p, k) = (dd[j] / s) / S.s[k];
-    }
-    int nvec = 1;
-    NKA_H(S, p, p) = 1.0;
+    for (int j = 1 + par.lane(); j < L; j += par.nlanes())
+      if (j != missing) NKA_H(S, p, X.ord[j]) = (dd[j] / s) / S.s[X.ord[j]];
+    par.sync();
     const double tol2 = S.vtol * S.vtol;
-    int pos = 1;                                   // list position of k as pass A saw it
-    // act[0..na-1] = the slots on the list before k, in list order (p first, then the survivors):
-    // walking it is walking the reference's list (`for j = first; j != k; j = next[j]`) without
-    // the dependent next[] loads, so the operand loads of consecutive terms overlap.
-    int act[NKA_MAXSLOT];
-    int na = 1;
-    act[0] = p;
-    for (int k = S.next[p]; k != NKA_NIL; k = S.next[k], ++pos) {
-      if (++nvec > S.mvec) {                       // :339-347
-        if (S.last != k) S.error = 1;
-        S.next[S.last] = S.free_;
-        S.free_ = k;
-        S.last = S.prev[k];
-        S.next[S.last] = NKA_NIL;
-        removed[k] = true;
-        if (pos < jr) jr = pos;
-        S.evicted_last = 1;
-        break;
+    nka_cholesky_column(S, X, 0, 1, L, missing, par);
+    par.sync();
+    for (int pos = 1; pos < L; ++pos) {            // the rows in list order: one decision each
+      if (lead) {
+        const int k = X.ord[pos];
+        X.newcol = 0;
+        if (++X.nvec > S.mvec) {                   // :339-347
+          if (S.last != k) S.error = 1;
+          S.next[S.last] = S.free_;
+          S.free_ = k;
+          S.last = S.prev[k];
+          S.next[S.last] = NKA_NIL;
+          X.removed[k] = 1;
+          if (pos < X.jr) X.jr = pos;
+          S.evicted_last = 1;
+          X.stop = 1;
+        } else if (pos == missing) {               // a drop made room: the skipped column matters
+          S.need_fixup = 1;
+          X.ret = 1;
+        } else {
+          const double hkk = X.hkk[k];
+          if (hkk - tol2 < S.min_margin) S.min_margin = hkk - tol2;
+          if (hkk > tol2) {                        // :362-363
+            NKA_H(S, k, k) = NKA_SQRT(hkk);
+            X.act[X.na++] = k;
+            X.newcol = 1;
+          } else {                                 // :364-379
+            const int pk = S.prev[k], nk = S.next[k];
+            S.next[pk] = nk;
+            if (nk == NKA_NIL) S.last = pk;
+            else S.prev[nk] = pk;
+            S.next[k] = S.free_;
+            S.free_ = k;
+            X.removed[k] = 1;
+            if (pos < X.jr) X.jr = pos;
+            --X.nvec;
+            ++S.ndrop_last;
+          }
+        }
       }
-      if (pos == missing) { S.need_fixup = 1; return 1; }   // a drop made room: the skipped column matters
-      double hkk = 1.0;                            // :350-360
-      const double* hk_raw = &NKA_H(S, 0, k);      // column k: raw Gram entries H(j,k) of newer slots j
-      double* hk = &NKA_H(S, k, 0);                // row k: the factor entries being formed
-      for (int jj = 0; jj < na; ++jj) {
-        const int j = act[jj];
-        const double* hj = &NKA_H(S, j, 0);
-        double hkj = hk_raw[j * NKA_MAXSLOT];
-        for (int ii = 0; ii < jj; ++ii) hkj -= hk[act[ii]] * hj[act[ii]];
-        hkj /= hj[j];
-        hk[j] = hkj;
-        hkk -= hkj * hkj;
-      }
-      if (hkk - tol2 < S.min_margin) S.min_margin = hkk - tol2;
-      if (hkk > tol2) {                            // :362-363
-        NKA_H(S, k, k) = NKA_SQRT(hkk);
-        act[na++] = k;
-      } else {                                     // :364-379
-        const int pk = S.prev[k], nk = S.next[k];
-        S.next[pk] = nk;
-        if (nk == NKA_NIL) S.last = pk;
-        else S.prev[nk] = pk;
-        S.next[k] = S.free_;
-        S.free_ = k;
-        removed[k] = true;
-        if (pos < jr) jr = pos;
-        k = pk;
-        --nvec;
-        ++S.ndrop_last;
-      }
+      par.sync();
+      if (X.ret) return 1;
+      if (X.stop) break;
+      if (X.newcol && pos + 1 < L) nka_cholesky_column(S, X, X.na - 1, pos + 1, L, missing, par);
+      par.sync();
     }
-    S.subspace = 1;
-    S.pending = 0;
+    if (lead) {
+      S.subspace = 1;
+      S.pending = 0;
+    }
+    par.sync();
   }
 
-  // Pairs that lost their newer neighbour are converted before pass B overwrites anything.
-  if (jr < L) nka_plan_materialise(S, ord, L, jr, removed);
-
-  // Step C: storage for the new vectors.  src-C/...c:391-394
-  if (S.free_ == NKA_NIL) { S.error = 2; return 0; }
-  const int nw = S.free_;
-  S.free_ = S.next[nw];
+  if (lead) {
+    // Pairs that lost their newer neighbour are converted before pass B overwrites anything.
+    if (X.jr < L) {
+      bool rem[NKA_MAXSLOT];
+      for (int k = 0; k < NKA_MAXSLOT; ++k) rem[k] = X.removed[k] != 0;
+      nka_plan_materialise(S, X.ord, L, X.jr, rem);
+    }
+    // Step C: storage for the new vectors.  src-C/...c:391-394
+    if (S.free_ == NKA_NIL) { S.error = 2; X.ret = 2; }
+    else {
+      X.nw = S.free_;
+      S.free_ = S.next[X.nw];
+      X.nl = 0;
+      for (int j = S.first; j != NKA_NIL; j = S.next[j]) X.lst[X.nl++] = j;   // the list after the update, newest first
+    }
+  }
+  par.sync();
+  if (X.ret) return 0;
 
   // Step D: projection.  src-C/...c:400-417
   NkaPlanB& B = S.planB;
-  B.newslot = nw;
-  B.has_pair = has_pair;
-  B.pslot = has_pair ? S.first : 0;
-  B.coef_p = 0.0;
-  B.nz = 0;
-  B.write_f = 0;
+  const int nl = X.nl;
   if (S.subspace) {
-    for (int j = 0; j < L; ++j)
-      if (!removed[ord[j]]) rhs[ord[j]] = fd[j] / S.s[ord[j]];        // <f, w_k>
-    int lst[NKA_MAXSLOT];                          // the list after the update, newest first
-    int nl = 0;
-    for (int j = S.first; j != NKA_NIL; j = S.next[j]) lst[nl++] = j;
-    for (int jj = 0; jj < nl; ++jj) {              // forward substitution, :405-411
-      const int j = lst[jj];
-      const double* hj = &NKA_H(S, j, 0);
-      double cj = rhs[j];
-      for (int ii = 0; ii < jj; ++ii) cj -= hj[lst[ii]] * S.c[lst[ii]];
-      S.c[j] = cj / hj[j];
+    for (int j = par.lane(); j < L; j += par.nlanes())
+      if (!X.removed[X.ord[j]]) X.rhs[X.ord[j]] = fd[j] / S.s[X.ord[j]];      // <f, w_k>
+    par.sync();
+    // forward substitution (:405-411): c_j = (rhs_j - sum_{i before j} h(j,i) c_i) / h(j,j), the
+    // subtractions applied to every later row as soon as c_i is known, i.e. in the reference's order
+    for (int jj = 0; jj < nl; ++jj) {
+      const int j = X.lst[jj];
+      if (lead) S.c[j] = X.rhs[j] / NKA_H(S, j, j);
+      par.sync();
+      const double cj = S.c[j];
+      for (int q = jj + 1 + par.lane(); q < nl; q += par.nlanes()) X.rhs[X.lst[q]] -= NKA_H(S, X.lst[q], j) * cj;
+      par.sync();
     }
-    for (int jj = nl - 1; jj >= 0; --jj) {         // backward substitution, :412-417
-      const int j = lst[jj];
-      double cj = S.c[j];
-      for (int ii = nl - 1; ii > jj; --ii) cj -= NKA_H(S, lst[ii], j) * S.c[lst[ii]];
-      S.c[j] = cj / NKA_H(S, j, j);
+    // backward substitution (:412-417): c_j = (c_j - sum_{i after j, from the last} h(i,j) c_i) / h(j,j)
+    for (int jj = nl - 1; jj >= 0; --jj) {
+      const int j = X.lst[jj];
+      if (lead) S.c[j] = S.c[j] / NKA_H(S, j, j);
+      par.sync();
+      const double cj = S.c[j];
+      for (int q = jj - 1 - par.lane(); q >= 0; q -= par.nlanes()) S.c[X.lst[q]] -= NKA_H(S, j, X.lst[q]) * cj;
+      par.sync();
     }
-    B.write_f = 1;
   }
   // Pass B streams the Z column of every pair that was on the list at entry: with the old
   // coefficient it rebuilds the pending correction Y, with the new one (0 if the pair left the
   // list) it forms the correction  f += sum_k c_k (v_k - w_k) = sum_k (c_k / s_k) Z[k]  (:419-424).
-  for (int j = pending_at_entry ? 1 : 0; j < L; ++j) {
-    const int k = ord[j];
-    B.zcol[B.nz] = k;
-    B.coefY[B.nz] = S.coefY[k];
-    B.coefN[B.nz] = (S.subspace && !removed[k]) ? S.c[k] / S.s[k] : 0.0;
-    ++B.nz;
+  const int z0 = X.pending_at_entry ? 1 : 0;
+  for (int j = z0 + par.lane(); j < L; j += par.nlanes()) {
+    const int k = X.ord[j];
+    B.zcol[j - z0] = k;
+    B.coefY[j - z0] = S.coefY[k];
+    B.coefN[j - z0] = (S.subspace && !X.removed[k]) ? S.c[k] / S.s[k] : 0.0;
   }
-  if (has_pair) B.coef_p = S.c[S.first] / S.s[S.first];
-  // remember how this call's correction y was assembled; the next pass B recomputes it
-  for (int k = 0; k <= S.mvec; ++k) S.coefY[k] = 0.0;
-  for (int i = 0; i < B.nz; ++i) S.coefY[B.zcol[i]] = B.coefN[i];
-  if (has_pair) S.coefY[S.first] = B.coef_p;
+  par.sync();
+  if (lead) {
+    const int nw = X.nw;
+    B.newslot = nw;
+    B.has_pair = X.has_pair;
+    B.pslot = X.has_pair ? S.first : 0;
+    B.nz = L > z0 ? L - z0 : 0;
+    B.write_f = S.subspace ? 1 : 0;
+    B.coef_p = X.has_pair ? S.c[S.first] / S.s[S.first] : 0.0;
+    // remember how this call's correction y was assembled; the next pass B recomputes it
+    for (int k = 0; k <= S.mvec; ++k) S.coefY[k] = 0.0;
+    for (int i = 0; i < B.nz; ++i) S.coefY[B.zcol[i]] = B.coefN[i];
+    if (X.has_pair) S.coefY[S.first] = B.coef_p;
 
-  // Step E: push the new slot, mark pending.  src-C/...c:432-443
-  S.prev[nw] = NKA_NIL;
-  S.next[nw] = S.first;
-  if (S.first == NKA_NIL) S.last = nw;
-  else S.prev[S.first] = nw;
-  S.first = nw;
-  S.pending = 1;
-  S.chained[nw] = 0;
-  ++S.ncalls;
+    // Step E: push the new slot, mark pending.  src-C/...c:432-443
+    S.prev[nw] = NKA_NIL;
+    S.next[nw] = S.first;
+    if (S.first == NKA_NIL) S.last = nw;
+    else S.prev[S.first] = nw;
+    S.first = nw;
+    S.pending = 1;
+    S.chained[nw] = 0;
+    ++S.ncalls;
 
-  nka_build_plan_a(S);
+    nka_build_plan_a(S);
+  }
+  par.sync();
   return 0;
 }
 

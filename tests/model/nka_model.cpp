@@ -21,6 +21,7 @@ struct Model {
   int mvec;
   std::vector<double> W, Z;
   NkaDevState S;
+  NkaStepScratch scratch;
   double dots[2 * NKA_MAXSLOT];
   // host-side bookkeeping mirrored from nka_capi.cu
   bool pending;
@@ -129,16 +130,16 @@ void model_accel_update(Model* m, double* f)
   if (L > 0) {
     pass_a(m, f);
     NkaDevState copy = m->S;                       // the device works on a staged copy
-    if (nka_state_step(copy, m->dots, NKA_MAXSLOT, 0)) {
+    if (nka_state_step(copy, m->scratch, m->dots, NKA_MAXSLOT, 0, NkaSerial())) {
       if (!may_skip) m->bound_violations++;        // the host must have queued the fix-up kernel
       m->S.need_fixup = 1;
       fixup(m, f);
       copy = m->S;
-      if (nka_state_step(copy, m->dots, NKA_MAXSLOT, 1)) m->bound_violations++;
+      if (nka_state_step(copy, m->scratch, m->dots, NKA_MAXSLOT, 1, NkaSerial())) m->bound_violations++;
     }
     m->S = copy;
   } else {
-    nka_state_step(m->S, m->dots, NKA_MAXSLOT, 1);
+    nka_state_step(m->S, m->scratch, m->dots, NKA_MAXSLOT, 1, NkaSerial());
   }
   pass_b(m, f);
   if (m->pending) m->ub_len = L + 1 < m->mvec + 1 ? L + 1 : m->mvec + 1;
