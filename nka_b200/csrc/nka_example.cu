@@ -274,7 +274,7 @@ __device__ __forceinline__ void tagged_send(uint4* slot, double v, unsigned tag)
 struct SsorEnt { double r, ac, axl, ayd, zo, zs, axr; };
 
 // What a step needs that does not depend on new values, formed one step ahead of use from raw
-// operands that were loaded RING steps ahead (so neither the loads nor these products sit on
+// operands that were copied EX_SSOR_DIST steps ahead (so neither the loads nor these products sit on
 // the dependent chain).  forward: a = r, b = axl, p0 = axr*z_old(j+1,k), p1 = ayu*z_old(j,k+1);
 // backward: a = r + axl*z_old(j-1,k), b = axr, p0 = ayd*z_old(j,k-1), p1 unused.
 struct SsorCooked { double a, b, p0, p1, po, ayd, ac; };
