@@ -114,3 +114,17 @@ def test_two_rank_slab_update_equals_serial_update():
         joined = np.concatenate([got[0]["outs"][t], got[1]["outs"][t]])
         assert np.linalg.norm(joined - full) <= 1e-12 * np.linalg.norm(full), t
         assert got[0]["nvec"][t] == got[1]["nvec"][t] == ser.num_vec()
+
+
+def test_row_slabs_tile_the_grid():
+    """nka_b200.example.row_slab: contiguous, balanced, complete (the slab example's partition)."""
+    from nka_b200.example import row_slab
+    for ny in (9, 50, 64, 131, 4096, 32768):
+        for world in (1, 2, 3, 4, 8):
+            if ny // world < 3:
+                continue
+            bounds = [row_slab(ny, world, r) for r in range(world)]
+            assert bounds[0][0] == 0 and bounds[-1][1] == ny
+            assert all(bounds[r][1] == bounds[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in bounds]
+            assert min(sizes) >= 3 and max(sizes) - min(sizes) <= 1
