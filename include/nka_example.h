@@ -92,6 +92,11 @@ int nka_example_solve (NKASYS, NKA acc, int nsweep, double omega, int maxitr, do
  * call), 1 = residual.  Same protocol as nka_timing_*. */
 /* Tuning aid: per-strip timeline of the last SSOR sweep (see nka_example.cu). Returns nstrips. */
 int nka_system_ssor_trace (NKASYS, int on, unsigned long long *out);
+/* Self-check: the SSOR sweep forms x/ac as (reciprocal of ac, off the dependent chain) + three
+ * chained operations; this compares that division with the device's IEEE division on nsamples
+ * generated operand pairs (edge mantissas, out-of-range exponents included) and returns the
+ * number of quotients that differ in any bit (must be 0). */
+unsigned long long nka_example_division_check (unsigned long long nsamples, unsigned long long seed, int device);
 void nka_system_timing_enable (NKASYS, int on);
 void nka_system_timing_read (NKASYS, double ms[2], unsigned long long count[2]);
 unsigned long long nka_system_launch_count (NKASYS);

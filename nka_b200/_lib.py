@@ -95,6 +95,7 @@ SYMBOLS = {
     "nka_example_solve": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double,
                                     _dp, C.POINTER(C.c_int)]),
     "nka_system_ssor_trace": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "nka_example_division_check": (C.c_ulonglong, [C.c_ulonglong, C.c_ulonglong, C.c_int]),
     "nka_system_timing_enable": (None, [C.c_void_p, C.c_int]),
     "nka_system_timing_read": (None, [C.c_void_p, _dp, C.POINTER(C.c_ulonglong)]),
     "nka_system_launch_count": (C.c_ulonglong, [C.c_void_p]),

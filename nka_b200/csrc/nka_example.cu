@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -572,6 +573,8 @@ __global__ void __launch_bounds__(64) ex_ssor_sweep(SsorParams P)
   }
 }
 
+#include "nka_ssor2.cuh"
+
 // ---------------------------------------------------------------------------
 // the handle
 // ---------------------------------------------------------------------------
@@ -604,6 +607,7 @@ struct nka_system {
   double* result_host = nullptr;   // pinned
   double* stage = nullptr;         // device scratch for the order conversions
   int ssor_grid = 0;
+  int ssor_kernel = 1;             // 1: ex_ssor_sweep, 2: ex_ssor_sweep2 (the chain on its own warp)
   bool bnd_dirty = true;
   int error = 0;
   unsigned long long launches = 0;
@@ -691,10 +695,19 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
   CUDA_CHECK(cudaMalloc(&sy->result, 2 * sizeof(double)));
   CUDA_CHECK(cudaMemsetAsync(sy->result, 0, 2 * sizeof(double), sy->stream));
   CUDA_CHECK(cudaMallocHost(&sy->result_host, 2 * sizeof(double)));
-  int occ = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep<1>, 64, 0));
-  int occb = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep<-1>, 64, 0));
+  const char* kv = getenv("NKA_SSOR_KERNEL");
+  sy->ssor_kernel = kv ? atoi(kv) : 1;
+  NKA_REQUIRE(sy->ssor_kernel == 1 || sy->ssor_kernel == 2, "NKA_SSOR_KERNEL must be 1 or 2");
+  int occ = 0, occb = 0;
+  if (sy->ssor_kernel == 2) {
+    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep2<1>, EX2_THREADS, EX2_SMEM_BYTES));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep2<-1>, EX2_THREADS, EX2_SMEM_BYTES));
+  } else {
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep<1>, 64, 0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep<-1>, 64, 0));
+  }
   if (occb < occ) occ = occb;
   NKA_REQUIRE(occ >= 1, "nka_system_init: the SSOR kernel does not fit on an SM");
   const int want = sy->nstrips;
@@ -907,11 +920,13 @@ extern "C" int nka_system_pc_ssor(NKASYS sy, int nsweep, double omega)
   for (int i = 0; i < nsweep; ++i) {
     P.zero_old = (i == 0) ? 1 : 0;                       // z = 0 start (:158): nothing to read yet
     P.tag_prev = sy->sweep_id; P.tag_cur = ++sy->sweep_id;
-    ex_ssor_sweep<1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
+    if (sy->ssor_kernel == 2) ex_ssor_sweep2<1><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
+    else ex_ssor_sweep<1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     P.zero_old = 0;
     P.tag_prev = sy->sweep_id; P.tag_cur = ++sy->sweep_id;
-    ex_ssor_sweep<-1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
+    if (sy->ssor_kernel == 2) ex_ssor_sweep2<-1><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
+    else ex_ssor_sweep<-1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     sy->launches += 2;
   }
@@ -957,6 +972,64 @@ extern "C" int nka_example_solve(NKASYS sy, NKA acc, int nsweep, double omega, i
     if (rnorm[itr] < tol * rnorm0) break;
   }
   return itr > maxitr ? maxitr : itr;
+}
+
+// ---------------------------------------------------------------------------
+// self-check of the split division used by ex_ssor_sweep2 (ex2_rcp / ex2_div_fast / ex2_div_safe)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ex_mix64(unsigned long long z)
+{
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// Pairs (x, b): random signs and mantissas (every 8th with a mantissa of all ones, all zeros, or
+// one bit off those: the cases where a quotient falls closest to a rounding boundary); exponents
+// within +-60 of 1 for most, anywhere (denormals, infinities, NaN included) for one in 16, so the
+// operand-range guard and the __ddiv_rn fallback are exercised too.
+__global__ void ex_division_check_kernel(unsigned long long nsamples, unsigned long long seed, unsigned long long* mismatches)
+{
+  unsigned long long bad = 0;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < nsamples;
+       i += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long h0 = ex_mix64(seed + 3 * i), h1 = ex_mix64(seed + 3 * i + 1), h2 = ex_mix64(seed + 3 * i + 2);
+    unsigned long long mx = h0 & 0x000FFFFFFFFFFFFFull, mb = h1 & 0x000FFFFFFFFFFFFFull;
+    if ((h2 & 7) == 0) {
+      const unsigned long long pat[4] = {0x000FFFFFFFFFFFFFull, 0ull, 0x000FFFFFFFFFFFFEull, 1ull};
+      mb = pat[(h2 >> 3) & 3];
+      if (h2 & 32) mx = pat[(h2 >> 6) & 3];
+    }
+    unsigned long long ex, eb;
+    if (((h2 >> 8) & 15) == 0) { ex = (h2 >> 12) & 0x7ff; eb = (h2 >> 23) & 0x7ff; }
+    else { ex = 963 + ((h2 >> 12) % 121); eb = 963 + ((h2 >> 23) % 121); }
+    const double x = __longlong_as_double((long long)(((h2 >> 40) & 1) << 63 | ex << 52 | mx));
+    const double b = __longlong_as_double((long long)(((h2 >> 41) & 1) << 63 | eb << 52 | mb));
+    const double want = __ddiv_rn(x, b);
+    double got = ex2_div_fast(x, b, ex2_rcp(b));
+    if (!(ex2_div_safe(b) && ex2_div_safe(x))) got = __ddiv_rn(x, b);
+    if (__double_as_longlong(want) != __double_as_longlong(got)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" unsigned long long nka_example_division_check(unsigned long long nsamples, unsigned long long seed, int device)
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    nka_fail(__FILE__, __LINE__, "no CUDA device: libnka_b200 has no CPU compute path");
+  if (device < 0) CUDA_CHECK(cudaGetDevice(&device));
+  DeviceGuard guard(device);
+  unsigned long long* d = nullptr;
+  CUDA_CHECK(cudaMalloc(&d, sizeof *d));
+  CUDA_CHECK(cudaMemset(d, 0, sizeof *d));
+  ex_division_check_kernel<<<148 * 8, 256>>>(nsamples, seed, d);
+  CUDA_CHECK(cudaGetLastError());
+  unsigned long long h = 0;
+  CUDA_CHECK(cudaMemcpy(&h, d, sizeof h, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return h;
 }
 
 extern "C" void nka_system_timing_enable(NKASYS sy, int on)

@@ -168,6 +168,15 @@ module nka_example_c
       integer(c_int) :: nstrips
     end function
 
+    !! unsigned long long nka_example_division_check (unsigned long long nsamples, unsigned long long seed, int device)
+    function nka_example_division_check(nsamples, seed, device) bind(C, name='nka_example_division_check') result(nbad)
+      import :: c_int, c_long_long
+      integer(c_long_long), value :: nsamples
+      integer(c_long_long), value :: seed
+      integer(c_int),       value :: device
+      integer(c_long_long) :: nbad
+    end function
+
     !! void nka_system_timing_enable (NKASYS, int on)
     subroutine nka_system_timing_enable(sys, on) bind(C, name='nka_system_timing_enable')
       import :: c_ptr, c_int

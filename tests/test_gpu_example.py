@@ -31,6 +31,23 @@ def _random_u(nx, ny, seed):
     return rng.uniform(0.0, 0.3, (ny, nx))          # a + u stays positive
 
 
+@pytest.fixture(params=[1, 2], ids=["sweep1", "sweep2"])
+def ssor_kernel(request, monkeypatch):
+    """Both SSOR kernels (NKA_SSOR_KERNEL is read when a System is created): ex_ssor_sweep and
+    ex_ssor_sweep2 (the dependent chain on a warp of its own)."""
+    monkeypatch.setenv("NKA_SSOR_KERNEL", str(request.param))
+    return request.param
+
+
+def test_ssor_division_identical():
+    """ex_ssor_sweep2 takes the reciprocal of the divisor off the dependent chain; the quotient
+    must be the device's IEEE quotient in every bit, out-of-range operands included."""
+    from nka_b200 import _lib
+    lib = _lib.load()
+    assert lib.nka_example_division_check(1 << 28, 12345, 0) == 0
+    assert lib.nka_example_division_check(1 << 24, 99, 0) == 0
+
+
 SHAPES = [(3, 3), (5, 4), (4, 9), (31, 17), (32, 32), (33, 70), (50, 50), (96, 40), (257, 129), (300, 300), (700, 64)]
 
 
@@ -56,7 +73,7 @@ def test_residual_and_coefficients_bit_identical(nx, ny, scaling):
 
 @pytest.mark.parametrize("nx,ny", SHAPES)
 @pytest.mark.parametrize("nsweep", [1, 2, 3])
-def test_pc_ssor_bit_identical_to_serial_gauss_seidel(nx, ny, nsweep):
+def test_pc_ssor_bit_identical_to_serial_gauss_seidel(nx, ny, nsweep, ssor_kernel):
     from nka_b200.example import System, FIELD_U, FIELD_R, FIELD_Z
     u = _random_u(nx, ny, nx * 77 + ny)
     sy = System(0.02, nx, ny, scaling=1)
@@ -98,7 +115,7 @@ def _golden_table(part):
     return [ln for ln in text.splitlines() if ":" in ln[:4] and ln[:3].strip().isdigit()]
 
 
-def test_example_on_device_reproduces_golden_accelerated_table():
+def test_example_on_device_reproduces_golden_accelerated_table(ssor_kernel):
     """src-F95/reference_output:5-31 == src-C/reference_output: 26 iterations, every line equal;
     no vector is ever dropped (num_vec 0,1,2,3,4,5,5,...), as in the reference run."""
     from nka_b200.example import System, Solver
@@ -112,7 +129,7 @@ def test_example_on_device_reproduces_golden_accelerated_table():
     so.delete(); sy.delete()
 
 
-def test_example_on_device_reproduces_golden_unaccelerated_table():
+def test_example_on_device_reproduces_golden_unaccelerated_table(ssor_kernel):
     """src-F95/reference_output:36-403: 367 iterations.  Without NKA every kernel on the path is
     bit-identical to the CPU code, so the norms agree to the last digits of the blocked sum."""
     from nka_b200.example import System, Solver
@@ -142,7 +159,7 @@ def test_example_on_device_f08_reference_output_lines():
         so.delete(); sy.delete()
 
 
-def test_example_rectangular_and_multi_cta_solve_matches_oracle_history():
+def test_example_rectangular_and_multi_cta_solve_matches_oracle_history(ssor_kernel):
     """A grid wider than one CTA's 256 columns, not a multiple of 32: same iteration count and
     residual history as the CPU oracle (NKA sums in another order: 1e-9 on the norms)."""
     from nka_b200.example import System, Solver
@@ -157,7 +174,7 @@ def test_example_rectangular_and_multi_cta_solve_matches_oracle_history():
     so.delete(); sy.delete()
 
 
-def test_full_size_4096_residual_and_ssor_bit_identical():
+def test_full_size_4096_residual_and_ssor_bit_identical(ssor_kernel):
     """BASELINE.json configs[1]: the 4096 x 4096 grid.  One residual and one 2-sweep SSOR
     application against the serial CPU loops, bit for bit; then 3 accelerated Picard iterations
     against the oracle's history."""
