@@ -700,10 +700,12 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
   NKA_REQUIRE(sy->ssor_kernel == 1 || sy->ssor_kernel == 2, "NKA_SSOR_KERNEL must be 1 or 2");
   int occ = 0, occb = 0;
   if (sy->ssor_kernel == 2) {
-    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
-    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep2<1>, EX2_THREADS, EX2_SMEM_BYTES));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep2<-1>, EX2_THREADS, EX2_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<-1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<-1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep2<1, false>, EX2_THREADS, EX2_SMEM_BYTES));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep2<-1, false>, EX2_THREADS, EX2_SMEM_BYTES));
   } else {
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep<1>, 64, 0));
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep<-1>, 64, 0));
@@ -920,12 +922,14 @@ extern "C" int nka_system_pc_ssor(NKASYS sy, int nsweep, double omega)
   for (int i = 0; i < nsweep; ++i) {
     P.zero_old = (i == 0) ? 1 : 0;                       // z = 0 start (:158): nothing to read yet
     P.tag_prev = sy->sweep_id; P.tag_cur = ++sy->sweep_id;
-    if (sy->ssor_kernel == 2) ex_ssor_sweep2<1><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
+    if (sy->ssor_kernel == 2 && P.trace) ex_ssor_sweep2<1, true><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
+    else if (sy->ssor_kernel == 2) ex_ssor_sweep2<1, false><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
     else ex_ssor_sweep<1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     P.zero_old = 0;
     P.tag_prev = sy->sweep_id; P.tag_cur = ++sy->sweep_id;
-    if (sy->ssor_kernel == 2) ex_ssor_sweep2<-1><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
+    if (sy->ssor_kernel == 2 && P.trace) ex_ssor_sweep2<-1, true><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
+    else if (sy->ssor_kernel == 2) ex_ssor_sweep2<-1, false><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
     else ex_ssor_sweep<-1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     sy->launches += 2;
