@@ -575,6 +575,28 @@ __global__ void __launch_bounds__(64) ex_ssor_sweep(SsorParams P)
 
 #include "nka_ssor2.cuh"
 
+// ex_ssor_sweep2 is compiled per direction x {trace off, on} x {one GPU, row slabs}
+template <typename F>
+static void ex2_for_each_variant(F f)
+{
+  f(ex_ssor_sweep2<1, false, false>); f(ex_ssor_sweep2<-1, false, false>);
+  f(ex_ssor_sweep2<1, false, true>);  f(ex_ssor_sweep2<-1, false, true>);
+  f(ex_ssor_sweep2<1, true, false>);  f(ex_ssor_sweep2<-1, true, false>);
+  f(ex_ssor_sweep2<1, true, true>);   f(ex_ssor_sweep2<-1, true, true>);
+}
+
+template <int DIR>
+static void ex2_launch(int grid, cudaStream_t stream, const SsorParams& P, bool slabs)
+{
+  if (P.trace) {
+    if (slabs) ex_ssor_sweep2<DIR, true, true><<<grid, EX2_THREADS, EX2_SMEM_BYTES, stream>>>(P);
+    else ex_ssor_sweep2<DIR, true, false><<<grid, EX2_THREADS, EX2_SMEM_BYTES, stream>>>(P);
+  } else {
+    if (slabs) ex_ssor_sweep2<DIR, false, true><<<grid, EX2_THREADS, EX2_SMEM_BYTES, stream>>>(P);
+    else ex_ssor_sweep2<DIR, false, false><<<grid, EX2_THREADS, EX2_SMEM_BYTES, stream>>>(P);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // the handle
 // ---------------------------------------------------------------------------
@@ -607,7 +629,7 @@ struct nka_system {
   double* result_host = nullptr;   // pinned
   double* stage = nullptr;         // device scratch for the order conversions
   int ssor_grid = 0;
-  int ssor_kernel = 1;             // 1: ex_ssor_sweep, 2: ex_ssor_sweep2 (the chain on its own warp)
+  int ssor_kernel = 2;             // 2: ex_ssor_sweep2 (the chain on a warp of its own); 1: ex_ssor_sweep (NKA_SSOR_KERNEL=1, kept for A/B timing)
   bool bnd_dirty = true;
   int error = 0;
   unsigned long long launches = 0;
@@ -696,16 +718,15 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
   CUDA_CHECK(cudaMemsetAsync(sy->result, 0, 2 * sizeof(double), sy->stream));
   CUDA_CHECK(cudaMallocHost(&sy->result_host, 2 * sizeof(double)));
   const char* kv = getenv("NKA_SSOR_KERNEL");
-  sy->ssor_kernel = kv ? atoi(kv) : 1;
+  sy->ssor_kernel = kv ? atoi(kv) : 2;
   NKA_REQUIRE(sy->ssor_kernel == 1 || sy->ssor_kernel == 2, "NKA_SSOR_KERNEL must be 1 or 2");
   int occ = 0, occb = 0;
   if (sy->ssor_kernel == 2) {
-    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
-    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<-1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
-    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
-    CUDA_CHECK(cudaFuncSetAttribute(ex_ssor_sweep2<-1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep2<1, false>, EX2_THREADS, EX2_SMEM_BYTES));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep2<-1, false>, EX2_THREADS, EX2_SMEM_BYTES));
+    ex2_for_each_variant([](auto kernel) {
+      CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
+    });
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep2<1, false, true>, EX2_THREADS, EX2_SMEM_BYTES));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep2<-1, false, true>, EX2_THREADS, EX2_SMEM_BYTES));
   } else {
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep<1>, 64, 0));
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep<-1>, 64, 0));
@@ -922,14 +943,12 @@ extern "C" int nka_system_pc_ssor(NKASYS sy, int nsweep, double omega)
   for (int i = 0; i < nsweep; ++i) {
     P.zero_old = (i == 0) ? 1 : 0;                       // z = 0 start (:158): nothing to read yet
     P.tag_prev = sy->sweep_id; P.tag_cur = ++sy->sweep_id;
-    if (sy->ssor_kernel == 2 && P.trace) ex_ssor_sweep2<1, true><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
-    else if (sy->ssor_kernel == 2) ex_ssor_sweep2<1, false><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
+    if (sy->ssor_kernel == 2) ex2_launch<1>(sy->ssor_grid, sy->stream, P, slabs);
     else ex_ssor_sweep<1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     P.zero_old = 0;
     P.tag_prev = sy->sweep_id; P.tag_cur = ++sy->sweep_id;
-    if (sy->ssor_kernel == 2 && P.trace) ex_ssor_sweep2<-1, true><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
-    else if (sy->ssor_kernel == 2) ex_ssor_sweep2<-1, false><<<sy->ssor_grid, EX2_THREADS, EX2_SMEM_BYTES, sy->stream>>>(P);
+    if (sy->ssor_kernel == 2) ex2_launch<-1>(sy->ssor_grid, sy->stream, P, slabs);
     else ex_ssor_sweep<-1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     sy->launches += 2;
