@@ -722,11 +722,14 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
   NKA_REQUIRE(sy->ssor_kernel == 1 || sy->ssor_kernel == 2, "NKA_SSOR_KERNEL must be 1 or 2");
   int occ = 0, occb = 0;
   if (sy->ssor_kernel == 2) {
-    ex2_for_each_variant([](auto kernel) {
+    // the grid must be co-resident whichever variant is launched: the smallest occupancy counts
+    occ = occb = 1 << 20;
+    ex2_for_each_variant([&occ](auto kernel) {
       CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EX2_SMEM_BYTES));
+      int o = 0;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, EX2_THREADS, EX2_SMEM_BYTES));
+      if (o < occ) occ = o;
     });
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep2<1, false, true>, EX2_THREADS, EX2_SMEM_BYTES));
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep2<-1, false, true>, EX2_THREADS, EX2_SMEM_BYTES));
   } else {
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_ssor_sweep<1>, 64, 0));
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occb, ex_ssor_sweep<-1>, 64, 0));
