@@ -90,6 +90,28 @@ def test_pc_ssor_bit_identical_to_serial_gauss_seidel(nx, ny, nsweep, ssor_kerne
     sy.delete()
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("nx,ny", [(9700, 7), (40000, 5)])
+def test_pc_ssor_more_strips_than_resident_ctas(nx, ny, ssor_kernel):
+    """Grids wider than 32 x (resident CTAs): every CTA then walks several strips in turn (the
+    32768-wide slab configuration does), so the hand-over barriers, mailbox and edge channels
+    must come back idle after each strip.  9700 columns = 304 strips > the 296 resident CTAs of
+    ex_ssor_sweep2; 40000 columns = 1250 strips > ex_ssor_sweep's residency too."""
+    from nka_b200.example import System, FIELD_U, FIELD_Z
+    u = _random_u(nx, ny, 4242)
+    sy = System(0.02, nx, ny, scaling=1)
+    sy.set(FIELD_U, u)
+    sy.residual()
+    orc = api.OracleSystem(nx, ny, 0.02, 1)
+    r = orc.residual(_pad(u))
+    for rep in range(2):
+        sy.pc_ssor(2, 1.4)
+        z = sy.get(FIELD_Z)
+        want = orc.pc_ssor(2, 1.4, r).reshape(ny, nx)
+        assert np.array_equal(z, want), (rep, float(np.abs(z - want).max()))
+    sy.delete()
+
+
 def test_update_then_residual_bit_identical():
     """u = u - r ; residual (src-F08/nka_example.F90:248-249) fused in one kernel."""
     from nka_b200.example import System, FIELD_U, FIELD_R, FIELD_Z
