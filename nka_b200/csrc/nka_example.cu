@@ -93,12 +93,19 @@ __device__ __forceinline__ double ex_warp_sum(double v)
 __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P)
 {
   const int nx = P.nx, ny = P.ny;
-  const int t = blockIdx.x;
-  const int jmin = t - (ny - 1) > 0 ? t - (ny - 1) : 0;
-  const int jmax = t < nx - 1 ? t : nx - 1;
-  const int p = blockIdx.y * EX_RES_THREADS + threadIdx.x;
+  // Work items = (diagonal t, chunk of EX_RES_THREADS cells of it).  A fixed grid of resident CTAs
+  // walks the items with a grid stride: one partial sum, one ticket and one block reduction per
+  // CTA instead of per item (one CTA per item spent about half of the kernel on 131072 tickets,
+  // fences and half-empty blocks at 4096^2).
+  const int nchunk = ((nx < ny ? nx : ny) + EX_RES_THREADS - 1) / EX_RES_THREADS;
+  const unsigned nitems = (unsigned)(nx + ny - 1) * (unsigned)nchunk;      // < 2^31: checked by nka_system_init_slab
   double rr = 0.0;
-  if (jmin + p <= jmax) {
+  for (unsigned item = blockIdx.x; item < nitems; item += gridDim.x) {
+    const int t = (int)(item / (unsigned)nchunk);
+    const int jmin = t - (ny - 1) > 0 ? t - (ny - 1) : 0;
+    const int jmax = t < nx - 1 ? t : nx - 1;
+    const int p = (int)(item - (unsigned)t * (unsigned)nchunk) * EX_RES_THREADS + threadIdx.x;
+    if (jmin + p > jmax) continue;
     const int j = jmin + p, k = t - j;
     const long long c = wf_base(t, nx, ny) + j;
     const long long bm = wf_base(t - 1, nx, ny), bp = wf_base(t + 1, nx, ny);
@@ -136,7 +143,7 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
     if (Zc) P.Unew[c] = uc;
     if (!hr) P.AXR[k] = axr;
     if (top) P.AYT[j] = ayu;
-    rr = r * r;
+    rr = __dadd_rn(rr, __dmul_rn(r, r));
   }
   // deterministic two-stage sum of r^2: warp tree, fixed-order across warps, one partial per
   // block, the last block (ticket) folds all partials in a fixed order
@@ -146,8 +153,8 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
   rr = ex_warp_sum(rr);
   if (lane == 0) red[warp] = rr;
   __syncthreads();
-  const unsigned nblk = gridDim.x * gridDim.y;
-  const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+  const unsigned nblk = gridDim.x;
+  const unsigned bid = blockIdx.x;
   if (threadIdx.x == 0) {
     double v = 0.0;
 #pragma unroll
@@ -628,6 +635,7 @@ struct nka_system {
   double* result = nullptr;        // device: [0] = sum r^2, [1] = error word of the SSOR kernels
   double* result_host = nullptr;   // pinned
   double* stage = nullptr;         // device scratch for the order conversions
+  int res_grid = 0;                // residual kernel: resident CTAs walking (diagonal, chunk) items
   int ssor_grid = 0;
   int ssor_kernel = 2;             // 2: ex_ssor_sweep2 (the chain on a warp of its own); 1: ex_ssor_sweep (NKA_SSOR_KERNEL=1, kept for A/B timing)
   bool bnd_dirty = true;
@@ -710,8 +718,16 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
   CUDA_CHECK(cudaMalloc(&sy->AYT, nx * sizeof(double)));
   sy->nstrips = (nx + 31) / 32;
   CUDA_CHECK(cudaMalloc(&sy->bnd, (size_t)sy->nstrips * ny * sizeof(unsigned long long)));
-  const size_t nblk = (size_t)(nx + ny - 1) * (((nx < ny ? nx : ny) + EX_RES_THREADS - 1) / EX_RES_THREADS);
-  CUDA_CHECK(cudaMalloc(&sy->partials, nblk * sizeof(double)));
+  {
+    const size_t nitems = (size_t)(nx + ny - 1) * (((nx < ny ? nx : ny) + EX_RES_THREADS - 1) / EX_RES_THREADS);
+    NKA_REQUIRE(nitems < ((size_t)1 << 31), "nka_system_init: grid too large");
+    int occ_res = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_res, ex_residual_kernel, EX_RES_THREADS, 0));
+    const char* wv = getenv("NKA_RES_WAVES");
+    const size_t cap = (size_t)sy->num_sms * (occ_res > 0 ? occ_res : 1) * (wv ? atoi(wv) : 4);
+    sy->res_grid = (int)(nitems < cap ? nitems : cap);
+  }
+  CUDA_CHECK(cudaMalloc(&sy->partials, (size_t)sy->res_grid * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&sy->ticket, sizeof(unsigned)));
   CUDA_CHECK(cudaMemsetAsync(sy->ticket, 0, sizeof(unsigned), sy->stream));
   CUDA_CHECK(cudaMalloc(&sy->result, 2 * sizeof(double)));
@@ -891,11 +907,9 @@ extern "C" double nka_system_residual(NKASYS sy, int subtract_z)
     rc |= g_nccl.GroupEnd();
     if (rc != 0) nka_fail(__FILE__, __LINE__, "nka_system_residual: NCCL edge-row exchange failed");
   }
-  const int maxlen = sy->nx < sy->ny ? sy->nx : sy->ny;
-  dim3 grid(sy->nx + sy->ny - 1, (maxlen + EX_RES_THREADS - 1) / EX_RES_THREADS);
   {
     ExScope t(sy, 1);
-    ex_residual_kernel<<<grid, EX_RES_THREADS, 0, sy->stream>>>(P);
+    ex_residual_kernel<<<sy->res_grid, EX_RES_THREADS, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     sy->launches += 1;
   }
