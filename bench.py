@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-host-memory e2e figure")
+    ap.add_argument("--no-probe", action="store_true", help="skip the cross-rank oracle parity probe")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the mvec 2/5/10/20 sweep (N = 1 only)")
     return ap.parse_args()
 
 
@@ -127,22 +130,25 @@ class ClockSampler:
 # --------------------------------------------------------------------------
 # the reference arm / cpu baseline: the reference's own serial C accel_update
 # --------------------------------------------------------------------------
-def cpu_reference_run(n_full: int, mvec: int, steps: int, warmup: int, budget_s: float):
-    """Time the reference's C accel_update (1 thread: the reference is serial) on a slice of
-    the workload small enough to finish in ~budget_s; returns updates/s extrapolated
-    linearly to n_full, with a description of the sample."""
+def cpu_reference_run(n_full: int, mvec: int, steps: int, warmup: int, budget_s: float, n_cap: int = 1 << 26):
+    """Time the reference's C accel_update (1 thread: the reference is serial) on a bounded sample
+    of the workload: the largest power-of-two length <= n_cap (2^26: BASELINE.md section 3; the
+    unmodified source overflows int at (mvec+1)*n >= 2^31, src-C/...c:235,241) whose whole run fits
+    in ~budget_s.  Returns updates/s scaled linearly to n_full, labelled as extrapolated, beside
+    the real per-call time of the sample."""
     import numpy as np
     from oracle import api
     calls = steps + warmup + mvec + 2
-    # ~1.0 s per update at n = 2^24, mvec = 10 on this class of host (BASELINE.md section 3)
-    per_elem = 1.0 / (1 << 24) * (2 * mvec + 4) / 24.0
+    # ~0.78 s per update at n = 2^24, mvec = 10 on this class of host (BENCH_r01), (8M+13) streams
+    per_elem = 0.8 / (1 << 24) * (8 * mvec + 13) / 93.0
     n_s = 1 << 16
-    while n_s * 2 <= min(n_full, 1 << 24) and (n_s * 2) * per_elem * calls <= budget_s:
+    while n_s * 2 <= min(n_full, n_cap) and (mvec + 1) * (n_s * 2) < 2 ** 31 \
+            and (n_s * 2) * per_elem * calls <= budget_s:
         n_s *= 2
     kind = "reference" if api.ref_lib() is not None else "port"
     acc = api.RefNKA(n_s, mvec, VTOL) if kind == "reference" else api.OracleNKA(n_s, mvec, VTOL)
     rng = np.random.default_rng(1234)
-    pool = [rng.uniform(-0.5, 0.5, n_s) for _ in range(mvec + 3)]
+    pool = [rng.random(n_s) - 0.5 for _ in range(mvec + 3)]
     k = 0
     for _ in range(mvec + 2 + warmup):
         acc.accel_update(pool[k % len(pool)])
@@ -155,27 +161,35 @@ def cpu_reference_run(n_full: int, mvec: int, steps: int, warmup: int, budget_s:
     nvec = acc.num_vec()
     acc.close()
     ups_sample = steps / dt
-    value = ups_sample * (n_s / n_full)
-    sample = ("%s C accel_update (gcc -O3, serial, default dp) timed at n=2^%d, mvec=%d, %d steady-state calls "
-              "(num_vec=%d); updates/s scaled linearly by n_sample/n to n=2^%d"
+    factor = n_full // n_s
+    value = ups_sample / factor
+    sample = ("%s C accel_update (gcc -O3 -DNDEBUG, serial, default dp) timed at n=2^%d, mvec=%d, %d steady-state "
+              "calls (num_vec=%d), %.1f ms per call; updates/s EXTRAPOLATED x1/%d (linear in n) to n=2^%d"
               % ("reference src-C" if kind == "reference" else "oracle port of the reference",
-                 n_s.bit_length() - 1, mvec, steps, nvec, n_full.bit_length() - 1))
+                 n_s.bit_length() - 1, mvec, steps, nvec, 1e3 * dt / steps, factor, n_full.bit_length() - 1))
     return {"value": value, "unit": "updates/s", "cores": 1, "kind": kind, "sample": sample,
-            "host_cores": os.cpu_count(), "ms_per_update_sample": 1e3 * dt / steps, "n_sample": n_s}
+            "host_cores": os.cpu_count(), "ms_per_update_sample": 1e3 * dt / steps, "n_sample": n_s,
+            "extrapolation_factor": factor, "updates_per_s_sample": ups_sample}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_reference_run(args.n, args.mvec, args.steps, args.warmup, budget_s=90.0)
+    res = cpu_reference_run(args.n, args.mvec, args.steps, args.warmup, budget_s=240.0)
     line = {
         "impl": "reference",
         "metric": "accel_update/sec", "value": res["value"], "unit": "updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 / res["value"], "higher_is_better": True, "scaling": "strong",
+        # what was really timed: one step = one reference call on the n_sample slice
+        "ms_per_step": res["ms_per_update_sample"],
+        "ms_per_step_extrapolated": 1e3 / res["value"],
+        "extrapolated": {"from_n": res["n_sample"], "to_n": args.n, "factor": res["extrapolation_factor"],
+                         "why": "the unmodified reference overflows int at (mvec+1)*n >= 2^31 "
+                                "(src-C/nonlinear_krylov_accelerator.c:235,241)"},
+        "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n_local=None),
+        "config": workload_config(args),
         "hbm_gbs": res["value"] * algorithmic_bytes(args.n, args.mvec) / 1e9,
         "cpu_baseline": res,
         "e2e": {"value": res["value"], "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -184,28 +198,182 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-def workload_config(args, n_local, comm_mode=None):
-    cfg = {
+def workload_config(args):
+    """Identical for both arms (the driver compares them)."""
+    return {
         "workload": "synthetic accel_update microbench (BASELINE.json configs[2]): n=2^%d fp64, mvec=%d, vtol=%g, "
                     "steady state (subspace full, one eviction per call), f_t i.i.d. uniform(-0.5,0.5)"
                     % (args.n.bit_length() - 1, args.mvec, VTOL),
         "n": args.n, "mvec": args.mvec, "vtol": VTOL,
         "l2": "inputs larger than L2: every column is %.0f MiB per GPU, no flush needed"
-              % ((n_local or args.n) * 8 / 2 ** 20),
-        "parallelism": ("row slabs, %d GPU(s), %s" % (args.gpus, {
-            "peer": "partial dot products summed across ranks inside pass A through NVLink peer memory "
-                    "(no collective launch)",
-            "nccl": "one 66-double NCCL all-reduce per update"}.get(comm_mode, "one small sum-allreduce per update")))
-                       if args.gpus > 1 else "single GPU",
+              % (args.n / max(args.gpus, 1) * 8 / 2 ** 20),
+        "parallelism": ("row slabs over %d GPUs, one small sum per update" % args.gpus) if args.gpus > 1
+                       else "single GPU",
     }
-    if n_local is not None:
-        cfg["n_local"] = n_local
-    return cfg
 
 
 # --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
+def bind_near_gpu(local_rank: int) -> dict:
+    """Run this process (and first-touch its host buffers) on the NUMA node the GPU hangs off:
+    with 8 ranks staging host vectors at once, buffers on the far socket share one inter-socket
+    link.  No-op when the platform does not expose the topology (VMs report node -1)."""
+    info = {"node": None, "bound": False}
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        with open(path) as fh:
+            node = int(fh.read().strip())
+        info["node"] = node
+        if node < 0:
+            return info
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as fh:
+            cpus = set()
+            for part in fh.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+            info["cpus"] = len(allowed)
+    except Exception as exc:                      # topology not visible: stay unbound
+        info["error"] = type(exc).__name__
+    return info
+
+
+def parity_probe(world, rank, local_rank):
+    """Before anything is timed: the N ranks together run two scenario sequences through the same
+    library path the timed region uses (row slabs, in-kernel cross-rank sum) and rank 0 compares the
+    joined corrections and every drop / eviction / relax decision with the CPU oracle
+    (oracle/api.py, the checker: bit-identical to the compiled reference).
+      A  picard_n500_m5_v2   vtol drops fire; odd slab sizes at N = 4, 8
+      B  i.i.d. n = 2^20 + 38, mvec = 10, 14 calls: strict 1e-12 against the long-double arbiter
+    Returns the dict for the JSON line on rank 0 (None elsewhere); ok=False fails the run."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import scenarios as S
+    from nka_b200 import NKA
+    from nka_b200.distributed import distributed_nka, slab_bounds
+
+    n_b = (1 << 20) + 38
+    cases = [("picard_n500_m5_v2",) + S.SCENARIOS["picard_n500_m5_v2"],
+             ("iid_n%d_m10" % n_b, n_b, 10, VTOL, lambda: S.iid(n_b, 14, 77))]
+    report = {"scenarios": [], "max_rel_err": 0.0, "decisions_equal": True, "ok": True, "comm_mode": None,
+              "ranks": world}
+    for name, n, mvec, vtol, mk in cases:
+        ops = mk()
+        if world > 1:
+            acc, lo, hi = distributed_nka(n, mvec, vtol, device=local_rank)
+        else:
+            acc, lo, hi = NKA(n, mvec, vtol, device=local_rank), 0, n
+        maxlen = max(slab_bounds(n, world, r)[1] - slab_bounds(n, world, r)[0] for r in range(world))
+        outs, decisions = [], []
+        for op in ops:
+            if op[0] == "update":
+                d = torch.zeros(maxlen, dtype=torch.float64, device="cuda")
+                d[: hi - lo].copy_(torch.from_numpy(np.ascontiguousarray(op[1][lo:hi])))
+                acc.accel_update(d[: hi - lo])
+                if world > 1:
+                    allv = torch.empty(world * maxlen, dtype=torch.float64, device="cuda")
+                    dist.all_gather_into_tensor(allv, d)
+                else:
+                    allv = d
+                if rank == 0:
+                    host = allv.cpu().numpy().reshape(world, maxlen)
+                    outs.append(np.concatenate([host[r, : slab_bounds(n, world, r)[1] - slab_bounds(n, world, r)[0]]
+                                                for r in range(world)]))
+                st = acc.state()
+                decisions.append((st["ndrop_last"], st["relaxed_last"], st["evicted_last"], st["error"], acc.num_vec()))
+            elif op[0] == "relax":
+                acc.relax()
+            else:
+                acc.restart()
+        mode = acc.comm_mode()
+        acc.delete()
+        if world > 1:
+            alld = [None] * world
+            dist.all_gather_object(alld, decisions)
+        else:
+            alld = [decisions]
+        if rank != 0:
+            continue
+        from oracle import api
+        inputs = [op[1] for op in ops if op[0] == "update"]
+        serial, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=0), ops)
+        arbiter, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=1), ops)
+        scales, tols = S.tolerances(serial, arbiter, inputs)
+        if name.startswith("iid"):
+            tols = [1e-12] * len(tols)
+        orc = api.OracleNKA(n, mvec, vtol, dotmode=0)
+        want_dec = []
+        for op in ops:
+            if op[0] == "update":
+                orc.accel_update(op[1].copy())
+                want_dec.append((orc.ndrop_last(), int(orc.relaxed_last()), int(orc.evicted_last()), 0, orc.num_vec()))
+            elif op[0] == "relax":
+                orc.relax()
+            else:
+                orc.restart()
+        dec_ok = all(list(map(tuple, d)) == want_dec for d in alld)
+        errs = [float(np.linalg.norm(o - a) / sc) for o, a, sc in zip(outs, arbiter, scales)]
+        err_ok = all(e <= t for e, t in zip(errs, tols))
+        report["scenarios"].append({"name": name, "n": n, "mvec": mvec, "vtol": vtol, "calls": len(inputs),
+                                    "drops": int(sum(d[0] for d in want_dec)), "max_rel_err": max(errs),
+                                    "tol": max(tols), "decisions_equal": dec_ok, "ok": bool(dec_ok and err_ok)})
+        report["max_rel_err"] = max(report["max_rel_err"], max(errs))
+        report["decisions_equal"] = report["decisions_equal"] and dec_ok
+        report["ok"] = report["ok"] and dec_ok and err_ok
+        report["comm_mode"] = mode
+    return report if rank == 0 else None
+
+
+def time_updates(acc, pool, k, steps, stream, torch):
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(steps):
+            acc.accel_update(pool[k % len(pool)]); k += 1
+        ev1.record(stream)
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1), k
+
+
+def mvec_sweep(n, pool, gen, stream, peak, torch):
+    """BASELINE.json configs[2]: mvec 2/5/10/20 at the same n, 5 steady-state steps each, outside the
+    headline's timed region (device-resident inputs; mvec = 20 needs 84 GiB of subspace)."""
+    from nka_b200 import NKA
+    out = []
+    for m in (2, 5, 10, 20):
+        need = (2 * (m + 1) + max(0, m + 3 - len(pool))) * n * 8
+        free, _ = torch.cuda.mem_get_info()
+        if free < need + (2 << 30):
+            out.append({"mvec": m, "skipped": "needs %.0f GiB, %.0f free" % (need / 2 ** 30, free / 2 ** 30)})
+            continue
+        while len(pool) < m + 3:
+            pool.append(torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) - 0.5)
+        acc = NKA(n, m, VTOL, stream=stream.cuda_stream)
+        k = 0
+        with torch.cuda.stream(stream):
+            for _ in range(m + 5):
+                acc.accel_update(pool[k % (m + 3)]); k += 1
+        torch.cuda.synchronize()
+        ms, k = time_updates(acc, pool[: m + 3], k, 5, stream, torch)
+        ups = 5 / (ms * 1e-3)
+        gbs = ups * algorithmic_bytes(n, m) / 1e9
+        out.append({"mvec": m, "updates_per_s": ups, "ms_per_update": ms / 5, "hbm_gbs": gbs, "frac": gbs / peak,
+                    "num_vec": acc.num_vec(), "steps": 5})
+        acc.delete()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -218,12 +386,37 @@ def run_ours(args):
             raise SystemExit("--gpus %d needs torchrun with %d processes (one per GPU)" % (args.gpus, args.gpus))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: nka_b200 has no CPU path")
+    numa = bind_near_gpu(local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from nka_b200 import NKA
     from nka_b200.distributed import distributed_nka
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- parity first: a fast kernel whose results differ from the reference's is not done ----
+    probe = None
+    if not args.no_probe:
+        probe = parity_probe(world, rank, local_rank)
+        flag = torch.tensor([1 if (probe is None or probe["ok"]) else 0], device="cuda")
+        if world > 1:
+            dist.broadcast(flag, src=0)
+        if int(flag.item()) == 0:
+            if rank == 0:
+                print(json.dumps({"error": "parity probe failed", "parity_probe": probe}))
+            raise SystemExit(3)
 
     n, m = args.n, args.mvec
     stream = torch.cuda.Stream()
@@ -240,11 +433,6 @@ def run_ours(args):
     gen = torch.Generator(device="cuda").manual_seed(1000 + rank)
     pool = [torch.rand(n_local, dtype=torch.float64, device="cuda", generator=gen) - 0.5 for _ in range(pool_n)]
     torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     k = 0
     with torch.cuda.stream(stream):
@@ -273,52 +461,84 @@ def run_ours(args):
         ev1.record(stream)
     barrier()
     t_wall1 = time.time()
-    elapsed_ms = ev0.elapsed_time(ev1)
+    elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = acc.launch_count() - launches0
     kt = acc.timing_read()
     acc.timing_enable(False)
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
     nvec_end = acc.num_vec()
     st = acc.state()
     geom = acc.launch_geometry()
+    comm_mode = acc.comm_mode()
 
-    # ---- e2e: the reference-facing entry point with host buffers ----
+    # ---- e2e: the reference-facing entry point with HOST buffers (H2D + kernels + D2H per step) ----
     e2e = None
     if not args.no_e2e:
+        import numpy as np
+        from nka_b200 import _lib
+        lib = _lib.load()
+        h = acc._handle()
+
+        def timed_host_calls(ptrs):
+            j = 0
+            for _ in range(2):
+                lib.nka_accel_update(h, ptrs[j % len(ptrs)]); j += 1
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps):
+                lib.nka_accel_update(h, ptrs[j % len(ptrs)]); j += 1     # synchronous: returns with f updated
+            torch.cuda.synchronize()
+            return max_over_ranks(time.perf_counter() - t0)
+
         host = [torch.empty(n_local, dtype=torch.float64, pin_memory=True) for _ in range(3)]
         for hb, src in zip(host, pool):
             hb.copy_(src)
         torch.cuda.synchronize()
-        from nka_b200 import _lib
-        lib = _lib.load()
-        h = acc._handle()
-        j = 0
-        for _ in range(2):
-            lib.nka_accel_update(h, host[j % 3].data_ptr()); j += 1
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            lib.nka_accel_update(h, host[j % 3].data_ptr()); j += 1     # H2D + kernels + D2H, synchronous
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+        dt = timed_host_calls([hb.data_ptr() for hb in host])
+
+        # the floor of any implementation: the coefficients need every element of f before any output
+        # element exists, so one H2D of the slab, then one D2H -- all ranks at once, bare copies
+        scratch = pool[0]
+        floor = 1e30
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            scratch.copy_(host[0], non_blocking=True)
+            host[0].copy_(scratch, non_blocking=True)
+            torch.cuda.synchronize()
+            floor = min(floor, max_over_ranks(time.perf_counter() - t0))
+
+        # pageable host memory: what an unmodified reference caller passes (src-C/nka_example.c:139, malloc)
+        pageable = None
+        if not args.no_pageable:
+            pg = [np.empty(n_local, dtype=np.float64) for _ in range(2)]
+            for a, hb in zip(pg, host):
+                a[:] = hb.numpy()
+            dtp = timed_host_calls([a.ctypes.data for a in pg])
+            pageable = {"value": args.e2e_steps / dtp, "unit": "updates/s", "ms_per_step": 1e3 * dtp / args.e2e_steps,
+                        "host_memory": "pageable (malloc), as src-C/nka_example.c:139 passes it"}
+            del pg
         e2e = {"value": args.e2e_steps / dt, "unit": "updates/s",
                "h2d_bytes_per_step": n_local * 8 * world, "d2h_bytes_per_step": n_local * 8 * world,
                "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
-               "api": "nka_accel_update(NKA, double* host_f) -- include/nonlinear_krylov_accelerator.h, pinned host f"}
+               "host_memory": "pinned (cudaHostAlloc)",
+               "pcie_floor_ms": 1e3 * floor, "frac_of_pcie_floor": floor / (dt / args.e2e_steps),
+               "pcie_floor": "bare cudaMemcpyAsync H2D then D2H of each rank's slab, all ranks at once, best of 3, "
+                             "max over ranks",
+               "pageable": pageable, "numa": numa,
+               "api": "nka_accel_update(NKA, double* host_f) -- include/nonlinear_krylov_accelerator.h"}
         del host
 
     if rank == 0:
         sampler.stop()
 
+    peak, peak_kind = measured_peak()
+    sweep = None
+    if rank == 0 and world == 1 and not args.no_sweep and n == N_FULL:
+        acc.delete()
+        acc = None
+        sweep = mvec_sweep(n, pool, gen, stream, peak, torch)
+
     if rank == 0:
-        peak, peak_kind = measured_peak()
         ups = args.steps / (elapsed_ms * 1e-3)
         algo = algorithmic_bytes(n, m)
         gbs = ups * algo / 1e9
@@ -351,8 +571,10 @@ def run_ours(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, n_local, acc.comm_mode()),
-            "comm_mode": acc.comm_mode(),
+            "config": workload_config(args),
+            "n_local": n_local,
+            "comm_mode": comm_mode,
+            "parity_probe": probe,
             "hbm_gbs": gbs, "roofline_frac_update": gbs / (peak * world),
             "roofline_update": {"algorithmic_bytes": algo, "formula": "(2M+4)*n*8", "achieved_gbs": gbs,
                                 "peak_gbs": peak * world, "frac": gbs / (peak * world),
@@ -372,13 +594,17 @@ def run_ours(args):
                 "geometry": geom,
             },
             "num_vec": nvec_end, "state_error": st["error"],
+            "mvec_sweep": sweep,
         }
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_reference_run(n, m, steps=5, warmup=0, budget_s=20.0)
+            del pool
+            torch.cuda.empty_cache()
+            line["cpu_baseline"] = cpu_reference_run(n, m, steps=5, warmup=0, budget_s=20.0, n_cap=1 << 24)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
-    acc.delete()
+    if acc is not None:
+        acc.delete()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

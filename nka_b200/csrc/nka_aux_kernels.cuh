@@ -30,7 +30,7 @@ nka_fixup_kernel(const double* __restrict__ f, const double* __restrict__ W, siz
   const double* w0 = W + (size_t)A.col[0] * ld;
   const double* wl = W + (size_t)A.col[jl] * ld;
   const double* wp = W + (size_t)A.col[jl - 1] * ld;
-  const bool sub = (A.submask >> jl) & 1u;
+  const bool sub = (A.submask >> jl) & 1ull;
   double acc[2] = {0.0, 0.0};
   const size_t stride = (size_t)gridDim.x * NKA_THREADS;
   for (size_t i = (size_t)blockIdx.x * NKA_THREADS + threadIdx.x; i < n; i += stride) {

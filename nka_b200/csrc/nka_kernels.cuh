@@ -347,7 +347,7 @@ __device__ __forceinline__ void nka_run_state_step(NkaStateStage& sm, NkaDevStat
 // ---------------------------------------------------------------------------
 template <int NC, int V, bool FULL>
 __device__ __forceinline__ void nka_pass_a_elem(const double* __restrict__ f, const double* const (&wcol)[NC],
-                                                size_t i, int ncol, unsigned submask, double (&acc)[2 * NC])
+                                                size_t i, int ncol, unsigned long long submask, double (&acc)[2 * NC])
 {
   using T = Vec<V>;
   const T x0 = T::ld_keep(f, i);          // f is read again by pass B: leave it in L2 if it fits
@@ -363,7 +363,7 @@ __device__ __forceinline__ void nka_pass_a_elem(const double* __restrict__ f, co
   for (int j = 0; j < NC; ++j) {
     T d;
     if (FULL) d = xs[j] - prev;
-    else d = ((submask >> j) & 1u) ? (xs[j] - prev) : xs[j];
+    else d = ((submask >> j) & 1ull) ? (xs[j] - prev) : xs[j];
     if (j == 0) d0 = d;
     d0.dot_into(d, acc[j]);
     x0.dot_into(d, acc[NC + j]);
@@ -380,7 +380,7 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
 {
   NKA_STAMP_MIN(0);
   const int ncol = S->planA.ncol - S->planA.skip_last;      // columns actually streamed
-  const unsigned submask = S->planA.submask;
+  const unsigned long long submask = S->planA.submask;
   const double* wcol[NC];
 #pragma unroll
   for (int j = 0; j < NC; ++j) wcol[j] = W + (size_t)S->planA.col[j < ncol ? j : 0] * ld;
@@ -392,7 +392,7 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
   const size_t nv = n / V;
   const size_t stride = (size_t)gridDim.x * NKA_THREADS_A;
   const size_t start = (size_t)blockIdx.x * NKA_THREADS_A + threadIdx.x;
-  const unsigned allbits = NC >= 32 ? 0xffffffffu : ((1u << NC) - 1u);
+  const unsigned long long allbits = (1ull << NC) - 1ull;          // NC <= NKA_MAXSLOT = 33
   const bool full = (ncol == NC) && ((submask & allbits) == allbits);
   if (full) {
     for (size_t i = start; i < nv; i += stride) nka_pass_a_elem<NC, V, true>(f, wcol, i, ncol, submask, acc);

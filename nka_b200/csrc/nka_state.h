@@ -50,7 +50,7 @@
 struct NkaPlanA {
   int ncol;          // list length on entry
   int skip_last;     // 1: pass A leaves out col[ncol-1] (it will be evicted unless a drop occurs)
-  unsigned submask;
+  unsigned long long submask;   // 64-bit: the list holds up to NKA_MAXSLOT = 33 positions
   int col[NKA_MAXSLOT];
 };
 
@@ -127,10 +127,10 @@ NKA_HD void nka_build_plan_a(NkaDevState& S)
 {
   NkaPlanA& A = S.planA;
   int j = 0;
-  unsigned mask = 0;
+  unsigned long long mask = 0;
   for (int k = S.first; k != NKA_NIL; k = S.next[k], ++j) {
     A.col[j] = k;
-    if (j == 0 ? S.pending : S.chained[k]) mask |= (1u << j);
+    if (j == 0 ? S.pending : S.chained[k]) mask |= (1ull << j);
   }
   A.ncol = j;
   A.submask = mask;

@@ -43,7 +43,7 @@ static void pass_a(Model* m, const double* f)
     double prev = f[i], d0 = 0.0;
     for (int j = 0; j < ncol; ++j) {
       const double x = m->W[(size_t)A.col[j] * m->ld + i];
-      const double d = ((A.submask >> j) & 1u) ? x - prev : x;
+      const double d = ((A.submask >> j) & 1ull) ? x - prev : x;
       if (j == 0) d0 = d;
       dd[j] += (long double)d0 * d;
       fd[j] += (long double)f[i] * d;
@@ -62,7 +62,7 @@ static void fixup(Model* m, const double* f)
   for (size_t i = 0; i < m->n; ++i) {
     const double d0 = m->W[(size_t)A.col[0] * m->ld + i] - f[i];
     const double xl = m->W[(size_t)A.col[jl] * m->ld + i];
-    const double dl = ((A.submask >> jl) & 1u) ? xl - m->W[(size_t)A.col[jl - 1] * m->ld + i] : xl;
+    const double dl = ((A.submask >> jl) & 1ull) ? xl - m->W[(size_t)A.col[jl - 1] * m->ld + i] : xl;
     dd += (long double)d0 * dl;
     fd += (long double)f[i] * dl;
   }

@@ -123,6 +123,18 @@ def mixed_stress(n, ncall, seed):
     return ops
 
 
+def fill_then_collinear(n, nfill, ncol, seed, eps=2e-3):
+    """nfill i.i.d. calls (fills the list: no drops), then ncol nearly collinear ones: vtol
+    drops fire while the list is at capacity, so the lazily skipped oldest column is needed
+    after all (the fix-up sweep) at the largest list position."""
+    rng = np.random.default_rng(seed)
+    ops = [_upd(rng.uniform(-0.5, 0.5, n)) for _ in range(nfill)]
+    g = rng.uniform(-0.5, 0.5, n)
+    for t in range(ncol):
+        ops.append(_upd(0.9 ** t * g * (1 + eps * rng.uniform(-1, 1, n))))
+    return ops
+
+
 # name -> (n, mvec, vtol, ops builder)
 SCENARIOS = {
     "iid_n64_m3":          (64, 3, 0.01, lambda: iid(64, 12, 1)),
@@ -148,6 +160,9 @@ SCENARIOS = {
     "iid_n2000_m16":       (2000, 16, 0.01, lambda: iid(2000, 40, 20)),
     "collinear_n400_m20":  (400, 20, 0.05, lambda: collinear(400, 48, 21, rho=0.9, eps=2e-1, delta=1e-3)),
     "iid_n513_m32":        (513, 32, 0.01, lambda: iid(513, 70, 22)),
+    # mvec = 32 with vtol drops at a full list: list position 32 (the 33rd) carries a chained bit
+    "fullthendrop_n700_m32": (700, 32, 0.1, lambda: fill_then_collinear(700, 36, 14, 24)),
+    "fullthendrop_n300_m4":  (300, 4, 0.1, lambda: fill_then_collinear(300, 8, 10, 25)),
 }
 
 

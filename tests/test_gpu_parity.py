@@ -20,6 +20,7 @@ import numpy as np
 import pytest
 
 import scenarios as S
+from parity_log import record_parity
 from oracle import api
 
 pytestmark = pytest.mark.gpu
@@ -54,6 +55,8 @@ def test_scenarios_match_oracle(name):
     orc = api.OracleNKA(n, mvec, vtol, dotmode=0)
     acc = NKA(n, mvec, vtol)
     it = 0
+    worst_arb = worst_ser = 0.0
+    ndrops = 0
     for op in ops:
         if op[0] == "update":
             fin = op[1]
@@ -66,7 +69,10 @@ def test_scenarios_match_oracle(name):
             assert st["error"] == 0
             assert (st["ndrop_last"], bool(st["relaxed_last"]), bool(st["evicted_last"])) == \
                    (orc.ndrop_last(), orc.relaxed_last(), orc.evicted_last()), (name, it)
+            ndrops += st["ndrop_last"]
             err = np.linalg.norm(got - arbiter[it]) / scales[it]
+            worst_arb = max(worst_arb, err)
+            worst_ser = max(worst_ser, np.linalg.norm(got - serial[it]) / scales[it])
             assert err <= tols[it], (name, it, err, tols[it])
             it += 1
         elif op[0] == "relax":
@@ -76,6 +82,23 @@ def test_scenarios_match_oracle(name):
         assert acc.num_vec() == orc.num_vec(), (name, it)
         assert acc.defined()
     acc.delete()
+    spread = max(np.linalg.norm(a - b) / sc for a, b, sc in zip(serial, arbiter, scales))
+    record_parity(name, n=n, mvec=mvec, vtol=vtol, calls=it, drops=ndrops,
+                  err_vs_arbiter=worst_arb, err_vs_serial_reference=worst_ser,
+                  reference_serial_vs_arbiter=spread, tol_used=max(tols),
+                  fraction_of_tol_used=worst_arb / max(tols))
+
+
+@pytest.mark.parametrize("name", ["fullthendrop_n700_m32", "fullthendrop_n300_m4", "picard_n500_m5_v2",
+                                  "collinear_n400_m20", "iid_n513_m32"])
+def test_scenarios_match_oracle_without_lazy_column(name):
+    """The same comparison with the lazy oldest column off (NKA_LAZY_LAST=0): pass A then streams
+    every list position, 33 of them at mvec = 32 -- position 32's chained bit needs the 64-bit mask."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests'); "
+            "import test_gpu_parity as T; T.test_scenarios_match_oracle(%r); print('ok')" % (ROOT, ROOT, name))
+    env = dict(os.environ, NKA_LAZY_LAST="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
 @pytest.mark.parametrize("name", ["iid_n64_m3", "iid_n1000_m10", "odd_n1023_m7", "n4097_m2", "mvec1_n17"])
