@@ -347,7 +347,7 @@ def time_updates(acc, pool, k, steps, stream, torch):
 
 
 def mvec_sweep(n, pool, gen, stream, peak, torch):
-    """BASELINE.json configs[2]: mvec 2/5/10/20 at the same n, 5 steady-state steps each, outside the
+    """BASELINE.json configs[2]: mvec 2/5/10/20 at the same n, 10 steady-state steps each, outside the
     headline's timed region (device-resident inputs; mvec = 20 needs 84 GiB of subspace)."""
     from nka_b200 import NKA
     out = []
@@ -365,11 +365,12 @@ def mvec_sweep(n, pool, gen, stream, peak, torch):
             for _ in range(m + 5):
                 acc.accel_update(pool[k % (m + 3)]); k += 1
         torch.cuda.synchronize()
-        ms, k = time_updates(acc, pool[: m + 3], k, 5, stream, torch)
-        ups = 5 / (ms * 1e-3)
+        steps = 10
+        ms, k = time_updates(acc, pool[: m + 3], k, steps, stream, torch)
+        ups = steps / (ms * 1e-3)
         gbs = ups * algorithmic_bytes(n, m) / 1e9
-        out.append({"mvec": m, "updates_per_s": ups, "ms_per_update": ms / 5, "hbm_gbs": gbs, "frac": gbs / peak,
-                    "num_vec": acc.num_vec(), "steps": 5})
+        out.append({"mvec": m, "updates_per_s": ups, "ms_per_update": ms / steps, "hbm_gbs": gbs, "frac": gbs / peak,
+                    "num_vec": acc.num_vec(), "steps": steps})
         acc.delete()
     return out
 
@@ -447,8 +448,6 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.15)
-    acc.timing_enable(True)
-    acc.timing_reset()
     launches0 = acc.launch_count()
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
@@ -463,6 +462,22 @@ def run_ours(args):
     t_wall1 = time.time()
     elapsed_ms = max_over_ranks(ev0.elapsed_time(ev1))
     launches = acc.launch_count() - launches0
+
+    # Per-kernel durations (roofline): the same steps again with a CUDA event pair around every
+    # launch (the library's timing mode, events on the handle's stream).  Kept out of the headline
+    # region because an event record between two kernels turns off their programmatic dependent
+    # launch overlap; `span_ms_per_step` is this region's own time per step, for comparison.
+    ksteps = max(1, min(args.steps, 50))
+    acc.timing_enable(True)
+    acc.timing_reset()
+    barrier()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(ksteps):
+            acc.accel_update(pool[k % pool_n]); k += 1
+        ev1.record(stream)
+    barrier()
+    span_ms = max_over_ranks(ev0.elapsed_time(ev1))
     kt = acc.timing_read()
     acc.timing_enable(False)
     nvec_end = acc.num_vec()
@@ -592,6 +607,9 @@ def run_ours(args):
                 "materialise": {"avg_ms": kt["materialise"]["ms"] / max(kt["materialise"]["count"], 1)},
                 "allreduce": {"avg_ms": kt["allreduce"]["ms"] / max(kt["allreduce"]["count"], 1)},
                 "geometry": geom,
+                "how": "CUDA event pair around every launch over %d further steps right after the timed region "
+                       "(events between kernels disable their dependent-launch overlap)" % ksteps,
+                "span_ms_per_step": span_ms / ksteps,
             },
             "num_vec": nvec_end, "state_error": st["error"],
             "mvec_sweep": sweep,

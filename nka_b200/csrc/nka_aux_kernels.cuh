@@ -10,6 +10,7 @@
 __global__ void __launch_bounds__(NKA_STATE_THREADS) nka_state_kernel(NkaDevState* S, const double* dots, int have_last)
 {
   __shared__ NkaStateStage sm;
+  nka_pdl_wait();
   nka_stage_in(sm, S, dots);
   nka_run_state_step(sm, S, have_last);
 }
@@ -24,6 +25,7 @@ nka_fixup_kernel(const double* __restrict__ f, const double* __restrict__ W, siz
                  NkaDevState* __restrict__ S, double* __restrict__ partials, unsigned* __restrict__ ticket,
                  double* __restrict__ dots, NkaPeerCtx* __restrict__ peer)
 {
+  nka_pdl_wait();
   if (!S->need_fixup) return;          // identical on every rank: they ran the state step on the same bits
   const NkaPlanA& A = S->planA;
   const int jl = A.ncol - 1;
@@ -98,6 +100,7 @@ __global__ void nka_set_lazy_kernel(NkaDevState* S, int lazy_last)
 __global__ void __launch_bounds__(NKA_THREADS)
 nka_materialise(double* W, size_t ld, size_t n, const NkaDevState* __restrict__ S)
 {
+  nka_pdl_wait();
   const int m = S->planM.n;
   if (m == 0) return;
   const size_t stride = (size_t)gridDim.x * NKA_THREADS;

@@ -38,13 +38,34 @@
 #endif
 static bool g_tables_ready = false;
 static int g_grid_per_sm_a = 0, g_grid_per_sm_b = 0;   // 0 = occupancy-derived; env overrides for tuning
+static bool g_pdl = true;                              // NKA_PDL=0: plain stream order (ablation)
 static void ensure_tables()
 {
   if (!g_tables_ready) {
     if (const char* e = getenv("NKA_GRID_PER_SM_A")) g_grid_per_sm_a = atoi(e);
     if (const char* e = getenv("NKA_GRID_PER_SM_B")) g_grid_per_sm_b = atoi(e);
+    if (const char* e = getenv("NKA_PDL")) g_pdl = atoi(e) != 0;
     g_tables_ready = true;
   }
+}
+
+// Launch with programmatic stream serialization (nka_kernels.cuh: nka_pdl_enter): the kernel's CTAs
+// may be scheduled while the previous kernel of the stream is still in its tail; they wait for its
+// completion before reading anything.
+template <typename... KArgs, typename... Args>
+static void launch_chained(void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, Args... args)
+{
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
 }
 
 // ---------------------------------------------------------------------------
@@ -474,10 +495,9 @@ static int launch_pass_a(NKA st, const UpdateShape& u, double* f, size_t off, si
   NKA_REQUIRE(row0 + grid <= st->max_grid, "pass A: too many partial rows");
   double* rows = st->partials + (size_t)row0 * 2 * u.NC;
   SpanScope t(st, T_PASS_A);
-  nka_get_pass_a(u.NC, u.V)<<<grid, NKA_THREADS_A, 0, st->stream>>>(
-      f + off, st->W + off, st->ld, len, st->S, rows, st->ticket, st->dots, u.fused ? 1 : 0, st->peer,
-      st->partials, final ? (unsigned)(row0 + grid) : 0u);
-  CUDA_CHECK(cudaGetLastError());
+  launch_chained(nka_get_pass_a(u.NC, u.V), grid, NKA_THREADS_A, st->stream,
+                 f + off, st->W + off, st->ld, len, st->S, rows, st->ticket, st->dots, u.fused ? 1 : 0, st->peer,
+                 st->partials, final ? (unsigned)(row0 + grid) : 0u);
   st->launches += 1;
   return grid;
 }
@@ -495,22 +515,19 @@ static void launch_mid(NKA st, const UpdateShape& u, double* f)
         if (rc != 0) nka_fail(__FILE__, __LINE__, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "ncclAllReduce failed");
       }
       SpanScope t(st, T_STATE);
-      nka_state_kernel<<<1, NKA_STATE_THREADS, 0, st->stream>>>(st->S, st->dots, 1);
-      CUDA_CHECK(cudaGetLastError());
+      launch_chained(nka_state_kernel, 1, NKA_STATE_THREADS, st->stream, st->S, st->dots, 1);
       st->launches += 1;
     } else if (u.may_skip) {
       // the oldest column was left out of pass A; this exits at once unless a vtol drop
       // (or the s == 0 guard) means it is needed after all
       SpanScope t(st, T_STATE);
-      nka_fixup_kernel<<<grid_for(st, 4, n, 1), NKA_THREADS, 0, st->stream>>>(f, st->W, st->ld, n, st->S, st->partials,
-                                                                             st->ticket, st->dots, st->peer);
-      CUDA_CHECK(cudaGetLastError());
+      launch_chained(nka_fixup_kernel, grid_for(st, 4, n, 1), NKA_THREADS, st->stream, f, st->W, st->ld, n, st->S,
+                     st->partials, st->ticket, st->dots, st->peer);
       st->launches += 1;
     }
   } else {
     SpanScope t(st, T_STATE);
-    nka_state_kernel<<<1, NKA_STATE_THREADS, 0, st->stream>>>(st->S, st->dots, 1);
-    CUDA_CHECK(cudaGetLastError());
+    launch_chained(nka_state_kernel, 1, NKA_STATE_THREADS, st->stream, st->S, st->dots, 1);
     st->launches += 1;
   }
 }
@@ -519,8 +536,8 @@ static void launch_pass_b(NKA st, const UpdateShape& u, double* f, size_t off, s
 {
   const int grid = grid_for(st, per_sm_b(st, u.nz, u.V, len), len, u.V, nka_threads_b(u.nz));
   SpanScope t(st, T_PASS_B);
-  nka_get_pass_b(u.nz, u.V)<<<grid, nka_threads_b(u.nz), 0, st->stream>>>(f + off, st->W + off, st->Z + off, st->ld, len, st->S);
-  CUDA_CHECK(cudaGetLastError());
+  launch_chained(nka_get_pass_b(u.nz, u.V), grid, nka_threads_b(u.nz), st->stream, f + off, st->W + off, st->Z + off,
+                 st->ld, len, st->S);
   st->launches += 1;
 }
 
@@ -650,8 +667,7 @@ extern "C" void nka_relax(NKA st)
   st->launches += 1;
   if (st->ub_len >= 2) {
     const int grid = grid_for(st, 4, st->vlen, 1);
-    nka_materialise<<<grid, NKA_THREADS, 0, st->stream>>>(st->W, st->ld, st->vlen, st->S);
-    CUDA_CHECK(cudaGetLastError());
+    launch_chained(nka_materialise, grid, NKA_THREADS, st->stream, st->W, st->ld, st->vlen, st->S);
     st->launches += 1;
   }
   st->pending = false;

@@ -180,6 +180,177 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
   }
 }
 
+// ---------------------------------------------------------------------------
+// residual, second formulation: every 1/(a+u) and every face coefficient formed ONCE
+// ---------------------------------------------------------------------------
+// ex_residual_kernel recomputes, in every cell, 1/(a+u) of the cell and its four neighbours and
+// the 2/s of its four faces: nine IEEE divisions per cell, 403 instructions per cell, instruction
+// bound at 27 % of the HBM rate (profiles/r1w_residual_ncu.txt).  But a face belongs to two cells
+// and both form it from the same operands in the same order (left/lower cell's term first,
+// src-F08/nka_example.F90:122-141), so computing it once and handing it to the neighbour gives
+// the same bits: three divisions per cell (1/(a+u), the left face, the lower face).
+//
+// One WARP walks a strip of 30 grid columns (lanes 1..30; lanes 0 and 31 redo the neighbouring
+// strips' edge columns, so no shared memory and no barrier is needed) down a band of consecutive
+// anti-diagonals: lane l holds column j = 30 s - 1 + l, at step tau it sits on cell (j, tau - j),
+// so the 32 lanes read and write 32 consecutive doubles of the wavefront-major arrays.  A lane
+// keeps u, tx = t*fx, ty = t*fy and its two faces of the previous two diagonals in registers; the
+// left neighbour's values come by shuffle.  At step tau the lane
+//   ingests u(tau) (prefetched EX_RS_PF steps ahead), forms t, tx, ty                    1 division
+//   forms its left face from lane-1's tx(tau-1) and its lower face from its own ty(tau-1)  2 divisions
+//   finishes cell (j, tau-1-j): right face = lane+1's new left face, upper face = its own new
+//   lower face; ac, r, r^2 exactly as the reference orders them (:115-117, :142).
+// Rows -1 / ny (the neighbouring slabs' edge rows, or nothing at a physical boundary) and columns
+// -1 / nx are walked like cells that are "absent": a face next to an absent cell sums one term.
+// Work items = (band, strip), handed out in order through an atomic counter; each item leaves its
+// own partial sum of r^2, folded in item order by the last CTA: run-to-run bit-stable.
+#define EX_RS_COLS 30
+#define EX_RS_THREADS 256
+#define EX_RS_PF 4
+
+struct ResStripParams {
+  ResParams p;
+  int nstrips, nbands, band;     // strips of 30 columns; bands of `band` diagonals per strip
+  unsigned* counter;             // next item
+};
+
+__global__ void __launch_bounds__(EX_RS_THREADS) ex_residual_strip_kernel(ResStripParams Q)
+{
+  const ResParams& P = Q.p;
+  const int nx = P.nx, ny = P.ny;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned nitems = (unsigned)Q.nstrips * (unsigned)Q.nbands;
+  const double* __restrict__ U = P.U;
+  const double* __restrict__ Zc = P.Zc;
+  const double* __restrict__ HLO = P.HLO;
+  const double* __restrict__ HHI = P.HHI;
+  const int tmax = nx + ny - 2;                       // last diagonal with cells
+
+  for (;;) {
+    unsigned item = 0;
+    if (lane == 0) item = atomicAdd(Q.counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= nitems) break;
+    const int b = (int)(item / (unsigned)Q.nstrips), s = (int)(item - (unsigned)b * (unsigned)Q.nstrips);
+    const int j = s * EX_RS_COLS - 1 + lane;
+    const bool cin = (unsigned)j < (unsigned)nx;
+    const bool mine = lane >= 1 && lane <= EX_RS_COLS && cin;
+    const int t0 = s * EX_RS_COLS + b * Q.band;                       // first diagonal this item finishes
+    int t1 = t0 + Q.band;                                             // one past the last
+    const int tend = s * EX_RS_COLS + EX_RS_COLS - 1 + ny;            // one past the strip's last diagonal with cells
+    if (t1 > tend) t1 = tend;
+    if (t1 > tmax + 1) t1 = tmax + 1;
+
+    // what a lane sees at (j, k): in-grid value, a neighbouring slab's edge row, or nothing
+    auto fetch = [&](int tau, long long base, double& ur, double& zr) {
+      const int k = tau - j;
+      const bool live = cin && tau <= t1;                             // nothing beyond the band's last step
+      const bool ing = live && (unsigned)k < (unsigned)ny;
+      const double* pu = U + (base + j);
+      bool pr = ing;
+      if (live && k == -1 && HLO) { pu = HLO + j; pr = true; }
+      if (live && k == ny && HHI) { pu = HHI + j; pr = true; }
+      ur = pr ? __ldg(pu) : 0.0;
+      zr = (ing && Zc) ? __ldg(Zc + (base + j)) : 0.0;
+    };
+    auto present = [&](int jj, int k) {
+      const bool c = (unsigned)jj < (unsigned)nx;
+      return c && ((unsigned)k < (unsigned)ny || (k == -1 && HLO != nullptr) || (k == ny && HHI != nullptr));
+    };
+    auto next_base = [&](int tau, long long base) -> long long {      // wf_base(tau + 1) from wf_base(tau)
+      return (tau >= 0 && tau <= tmax - 1) ? base + wf_step(tau, nx, ny) : 0;
+    };
+
+    // prefetch ring
+    double ub[EX_RS_PF], zb[EX_RS_PF];
+    int tf = t0 - 1;
+    long long basef = (tf >= 0 && tf <= tmax) ? wf_base(tf, nx, ny) : 0;
+#pragma unroll
+    for (int i = 0; i < EX_RS_PF; ++i) {
+      fetch(tf, basef, ub[i], zb[i]);
+      basef = next_base(tf, basef);
+      ++tf;
+    }
+
+    double u_pp = 0.0, u_p = 0.0, tx_p = 0.0, ty_p = 0.0, fx_p = 1.0, fy_p = 1.0;
+    long long base_c = (t0 - 1 >= 0 && t0 - 1 <= tmax) ? wf_base(t0 - 1, nx, ny) : 0, base_p = 0;
+    double rr = 0.0;
+    for (int tau0 = t0 - 1; tau0 <= t1; tau0 += EX_RS_PF) {
+#pragma unroll
+      for (int i = 0; i < EX_RS_PF; ++i) {
+        const int tau = tau0 + i;
+        if (tau <= t1) {                                               // warp-uniform
+          const int k = tau - j;
+          const bool pc = present(j, k);
+          const double u_n = Zc ? __dsub_rn(ub[i], zb[i]) : ub[i];    // u = u - r : F08 :248 (z = 0 outside the grid)
+          fetch(tf, basef, ub[i], zb[i]);                              // refill the slot, EX_RS_PF diagonals ahead
+          basef = next_base(tf, basef);
+          ++tf;
+          // update_system (:122-145)
+          const double tc = __ddiv_rn(1.0, __dadd_rn(P.a, u_n));
+          const double tx_n = __dmul_rn(tc, P.fx), ty_n = __dmul_rn(tc, P.fy);
+          const double tx_l = __shfl_up_sync(0xffffffffu, tx_p, 1);    // (j-1, k) sits on diagonal tau-1
+          const bool pl = present(j - 1, k), pd = present(j, k - 1);
+          const double sx = (pl && pc) ? __dadd_rn(tx_l, tx_n) : (pl ? tx_l : tx_n);
+          const double sy = (pd && pc) ? __dadd_rn(ty_p, ty_n) : (pd ? ty_p : ty_n);
+          const double fx_n = __ddiv_rn(2.0, sx);                      // left face of (j, k)
+          const double fy_n = __ddiv_rn(2.0, sy);                      // lower face of (j, k)
+          // finish cell (j, k-1) on diagonal tau-1
+          const double u_l = __shfl_up_sync(0xffffffffu, u_pp, 1);     // (j-1, k-1): diagonal tau-2
+          const double u_r = __shfl_down_sync(0xffffffffu, u_n, 1);    // (j+1, k-1): diagonal tau
+          const double axr = __shfl_down_sync(0xffffffffu, fx_n, 1);   // left face of (j+1, k-1)
+          const int kc = k - 1;
+          if (mine && tau - 1 >= t0 && (unsigned)kc < (unsigned)ny) {
+            const double axl = fx_p, ayd = fy_p, ayu = fy_n;
+            const double ac = __dadd_rn(__dadd_rn(__dadd_rn(axl, axr), ayd), ayu);        // :142
+            double r = __dmul_rn(ac, u_p);                                                  // :115-117, left to right
+            r = __dsub_rn(r, __dmul_rn(axl, u_l));
+            r = __dsub_rn(r, __dmul_rn(axr, u_r));
+            r = __dsub_rn(r, __dmul_rn(ayd, u_pp));
+            r = __dsub_rn(r, __dmul_rn(ayu, u_n));
+            r = __dsub_rn(r, P.q);
+            const long long c = base_p + j;
+            P.R[c] = r; P.AXL[c] = axl; P.AYD[c] = ayd; P.AC[c] = ac;
+            if (Zc) P.Unew[c] = u_p;
+            if (j == nx - 1) P.AXR[kc] = axr;
+            if (kc == ny - 1) P.AYT[j] = ayu;
+            rr = __dadd_rn(rr, __dmul_rn(r, r));
+          }
+          u_pp = u_p; u_p = pc ? u_n : 0.0;
+          tx_p = tx_n; ty_p = ty_n; fx_p = fx_n; fy_p = fy_n;
+          base_p = base_c;
+          base_c = next_base(tau, base_c);
+        }
+      }
+    }
+    rr = ex_warp_sum(rr);
+    if (lane == 0) P.partials[item] = rr;
+  }
+
+  // the last CTA folds the items' partial sums in item order
+  __shared__ double red[EX_RS_THREADS / 32];
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(P.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double v = 0.0;
+  for (unsigned i = threadIdx.x; i < nitems; i += EX_RS_THREADS) v += __ldcg(P.partials + i);
+  v = ex_warp_sum(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+#pragma unroll
+    for (int w = 0; w < EX_RS_THREADS / 32; ++w) sum += red[w];
+    *P.sumsq = sum;
+    *P.ticket = 0u;
+    *Q.counter = 0u;
+  }
+}
+
 // Row slabs: the slab's first and last rows of u (after u <- u - z, formed exactly as the residual
 // kernel will form it) packed for the neighbouring ranks.
 __global__ void ex_pack_rows_kernel(const double* __restrict__ U, const double* __restrict__ Zc, int nx, int ny,
@@ -636,6 +807,9 @@ struct nka_system {
   double* result_host = nullptr;   // pinned
   double* stage = nullptr;         // device scratch for the order conversions
   int res_grid = 0;                // residual kernel: resident CTAs walking (diagonal, chunk) items
+  int res_kernel = 2;              // 2: ex_residual_strip_kernel (3 divisions per cell); 1: ex_residual_kernel (NKA_RESIDUAL_KERNEL=1, A/B)
+  int rs_grid = 0, rs_strips = 0, rs_bands = 0, rs_band = 0;
+  unsigned* rs_counter = nullptr;
   int ssor_grid = 0;
   int ssor_kernel = 2;             // 2: ex_ssor_sweep2 (the chain on a warp of its own); 1: ex_ssor_sweep (NKA_SSOR_KERNEL=1, kept for A/B timing)
   bool bnd_dirty = true;
@@ -727,7 +901,36 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
     const size_t cap = (size_t)sy->num_sms * (occ_res > 0 ? occ_res : 1) * (wv ? atoi(wv) : 4);
     sy->res_grid = (int)(nitems < cap ? nitems : cap);
   }
-  CUDA_CHECK(cudaMalloc(&sy->partials, (size_t)sy->res_grid * sizeof(double)));
+  size_t npartials = (size_t)sy->res_grid;
+  {
+    // strip formulation: items = (band of diagonals, strip of 30 columns), a few per resident warp
+    const char* rk = getenv("NKA_RESIDUAL_KERNEL");
+    sy->res_kernel = rk ? atoi(rk) : 2;
+    NKA_REQUIRE(sy->res_kernel == 1 || sy->res_kernel == 2, "NKA_RESIDUAL_KERNEL must be 1 or 2");
+    int occ = 0;
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ex_residual_strip_kernel, EX_RS_THREADS, 0));
+    if (occ < 1) occ = 1;
+    sy->rs_strips = (nx + EX_RS_COLS - 1) / EX_RS_COLS;
+    const int ndiag = ny + EX_RS_COLS - 1;                             // diagonals a strip has cells on
+    const long long warps = (long long)sy->num_sms * occ * (EX_RS_THREADS / 32);
+    int per_warp = 4;                                                  // items per resident warp aimed at
+    if (const char* e = getenv("NKA_RES_ITEMS_PER_WARP")) if (atoi(e) > 0) per_warp = atoi(e);
+    long long bands = (warps * per_warp + sy->rs_strips - 1) / sy->rs_strips;
+    int band = (int)((ndiag + bands - 1) / (bands > 0 ? bands : 1));
+    if (band < 32) band = 32;                                          // two prologue diagonals per band: <= 6 % redone
+    if (const char* e = getenv("NKA_RES_BAND")) if (atoi(e) > 0) band = atoi(e);
+    sy->rs_band = band;
+    sy->rs_bands = (ndiag + band - 1) / band;
+    const size_t items = (size_t)sy->rs_strips * sy->rs_bands;
+    NKA_REQUIRE(items < ((size_t)1 << 31), "nka_system_init: grid too large");
+    const size_t ctas = (items + EX_RS_THREADS / 32 - 1) / (EX_RS_THREADS / 32);
+    const size_t cap = (size_t)sy->num_sms * occ;
+    sy->rs_grid = (int)(ctas < cap ? ctas : cap);
+    if (items > npartials) npartials = items;
+    CUDA_CHECK(cudaMalloc(&sy->rs_counter, sizeof(unsigned)));
+    CUDA_CHECK(cudaMemsetAsync(sy->rs_counter, 0, sizeof(unsigned), sy->stream));
+  }
+  CUDA_CHECK(cudaMalloc(&sy->partials, npartials * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&sy->ticket, sizeof(unsigned)));
   CUDA_CHECK(cudaMemsetAsync(sy->ticket, 0, sizeof(unsigned), sy->stream));
   CUDA_CHECK(cudaMalloc(&sy->result, 2 * sizeof(double)));
@@ -769,7 +972,7 @@ extern "C" void nka_system_delete(NKASYS sy)
   cudaFree(sy->trace);
   if (sy->comm) { nka_ipc_unmap(sy->comm, sy->zbox_mapped); nka_comm_release(sy->comm); }
   cudaFree(sy->zbox); cudaFree(sy->halo_u_lo); cudaFree(sy->halo_u_hi); cudaFree(sy->send_lo); cudaFree(sy->send_hi);
-  cudaFree(sy->partials); cudaFree(sy->ticket); cudaFree(sy->result); cudaFree(sy->stage);
+  cudaFree(sy->partials); cudaFree(sy->ticket); cudaFree(sy->result); cudaFree(sy->stage); cudaFree(sy->rs_counter);
   cudaFreeHost(sy->result_host);
   delete sy;
 }
@@ -909,7 +1112,13 @@ extern "C" double nka_system_residual(NKASYS sy, int subtract_z)
   }
   {
     ExScope t(sy, 1);
-    ex_residual_kernel<<<sy->res_grid, EX_RES_THREADS, 0, sy->stream>>>(P);
+    if (sy->res_kernel == 2) {
+      ResStripParams Q;
+      Q.p = P; Q.nstrips = sy->rs_strips; Q.nbands = sy->rs_bands; Q.band = sy->rs_band; Q.counter = sy->rs_counter;
+      ex_residual_strip_kernel<<<sy->rs_grid, EX_RS_THREADS, 0, sy->stream>>>(Q);
+    } else {
+      ex_residual_kernel<<<sy->res_grid, EX_RES_THREADS, 0, sy->stream>>>(P);
+    }
     CUDA_CHECK(cudaGetLastError());
     sy->launches += 1;
   }

@@ -142,6 +142,21 @@ __device__ __forceinline__ double nka_warp_sum(double v)
   return v;
 }
 
+// Programmatic dependent launch (sm_90+).  The kernels of the update chain (pass A -> fix-up ->
+// pass B) are launched with the programmatic-stream-serialization attribute and begin with
+// `griddepcontrol.wait`, which blocks until the previous grid has completed and its memory is
+// visible; nothing is read before it.  Pass A -- the one kernel with a serial tail: ticket, fold,
+// cross-rank exchange, scalar state step, ~24 us on one CTA -- issues `launch_dependents` when its
+// streaming loop is done, so the next kernel's CTAs are scheduled onto the idle SMs during that
+// tail and its launch latency disappears (-6 us per update: 0.320 -> 0.314 ms at n = 2^24, mvec = 5;
+// profiles/r2d_pdl_ab.jsonl).  Only when the kernel that follows is one of ours (fused mode): a
+// library kernel (NCCL) does not wait.  Triggering at the START of every kernel was tried first:
+// the parked CTAs of the dependents then sit beside pass A's streaming CTAs and cost 4-6 %
+// (profiles/r2b_pdl_ab_early_trigger.jsonl), and results were wrong -- not kept.
+// Without the attribute both instructions are no-ops.
+__device__ __forceinline__ void nka_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void nka_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ unsigned long long nka_globaltimer()
 {
   unsigned long long t;
@@ -210,7 +225,17 @@ __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* 
   __threadfence();
   for (int j = warp; j < K; j += THREADS / 32) {
     double v = 0.0;
-    for (unsigned b = lane; b < fold_rows; b += 32) v += __ldcg(&fold_base[(size_t)b * K + j]);
+    // the same left-to-right sum as a plain loop, with the (independent) loads of eight rows in
+    // flight at once: at 1184 rows the plain loop paid 37 L2 round trips per value (16 us)
+    unsigned b = lane;
+    for (; b + 7 * 32 < fold_rows; b += 8 * 32) {
+      double t[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t[u] = __ldcg(&fold_base[(size_t)(b + 32 * u) * K + j]);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += t[u];
+    }
+    for (; b < fold_rows; b += 32) v += __ldcg(&fold_base[(size_t)b * K + j]);
     v = nka_warp_sum(v);
     if (lane == 0) out(j, v);
   }
@@ -378,6 +403,7 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
            double* __restrict__ dots, int fuse_state, NkaPeerCtx* __restrict__ peer,
            const double* __restrict__ fold_base, unsigned fold_rows)
 {
+  nka_pdl_wait();
   NKA_STAMP_MIN(0);
   const int ncol = S->planA.ncol - S->planA.skip_last;      // columns actually streamed
   const unsigned long long submask = S->planA.submask;
@@ -402,6 +428,7 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
   if (V == 2 && (n & 1) && start == 0) nka_pass_a_elem<NC, 1, false>(f, wcol, n - 1, ncol, submask, acc);
 
   NKA_STAMP_MAX(1);
+  if (fuse_state) nka_pdl_trigger();   // the next kernel (fix-up / pass B: both wait) may be scheduled during the tail
   __shared__ NkaStateStage sm;     // used by the last CTA only
   __shared__ double xv[2 * NC];
   const bool last = nka_grid_reduce<2 * NC, NKA_THREADS_A>(acc, partials, ticket, fold_base, fold_rows,
@@ -486,6 +513,7 @@ __global__ void __launch_bounds__(nka_threads_b(NZ), NKA_MINB_B)
 nka_pass_b(double* __restrict__ f, double* W, double* Z, size_t ld, size_t n, const NkaDevState* __restrict__ S)
 {
   constexpr int NZA = NZ > 0 ? NZ : 1;
+  nka_pdl_wait();
   const NkaPlanB* B = &S->planB;
   const int nz = B->nz, has_pair = B->has_pair, write_f = B->write_f;
   double* wnew = W + (size_t)B->newslot * ld;
