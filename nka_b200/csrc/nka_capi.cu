@@ -38,27 +38,34 @@
 #endif
 static bool g_tables_ready = false;
 static int g_grid_per_sm_a = 0, g_grid_per_sm_b = 0;   // 0 = occupancy-derived; env overrides for tuning
-static bool g_pdl = true;                              // NKA_PDL=0: plain stream order (ablation)
+#ifdef NKA_EXPERIMENT_PDL
+static bool g_pdl = true;                              // tuning builds only (nka_kernels.cuh: not kept); NKA_PDL=0 turns it off
+#else
+static const bool g_pdl = false;
+#endif
+static bool g_pass_b_tma = false;                      // NKA_PASS_B_TMA=1: the cp.async.bulk staging experiment
 static void ensure_tables()
 {
   if (!g_tables_ready) {
     if (const char* e = getenv("NKA_GRID_PER_SM_A")) g_grid_per_sm_a = atoi(e);
     if (const char* e = getenv("NKA_GRID_PER_SM_B")) g_grid_per_sm_b = atoi(e);
+#ifdef NKA_EXPERIMENT_PDL
     if (const char* e = getenv("NKA_PDL")) g_pdl = atoi(e) != 0;
+#endif
+    if (const char* e = getenv("NKA_PASS_B_TMA")) g_pass_b_tma = atoi(e) != 0;
     g_tables_ready = true;
   }
 }
 
-// Launch with programmatic stream serialization (nka_kernels.cuh: nka_pdl_enter): the kernel's CTAs
-// may be scheduled while the previous kernel of the stream is still in its tail; they wait for its
-// completion before reading anything.
+// Plain stream-ordered launch.  (Tuning builds with -DNKA_EXPERIMENT_PDL add the programmatic stream
+// serialization attribute: see nka_kernels.cuh, an experiment that was not kept.)
 template <typename... KArgs, typename... Args>
-static void launch_chained(void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, Args... args)
+static void launch_chained_smem(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args)
 {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)block);
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -66,6 +73,12 @@ static void launch_chained(void (*kernel)(KArgs...), int grid, int block, cudaSt
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 1 : 0;
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+
+template <typename... KArgs, typename... Args>
+static void launch_chained(void (*kernel)(KArgs...), int grid, int block, cudaStream_t stream, Args... args)
+{
+  launch_chained_smem(kernel, grid, block, 0, stream, args...);
 }
 
 // ---------------------------------------------------------------------------
@@ -534,8 +547,18 @@ static void launch_mid(NKA st, const UpdateShape& u, double* f)
 
 static void launch_pass_b(NKA st, const UpdateShape& u, double* f, size_t off, size_t len)
 {
-  const int grid = grid_for(st, per_sm_b(st, u.nz, u.V, len), len, u.V, nka_threads_b(u.nz));
   SpanScope t(st, T_PASS_B);
+  if (g_pass_b_tma && u.V == 2 && len % 2 == 0 && len > 0) {
+    int threads = 0, smem = 0;
+    if (PassBFn k = nka_get_pass_b_tma(u.nz, &threads, &smem)) {
+      const size_t ntiles = (len + 511) / 512;
+      const int grid = (int)(ntiles < (size_t)st->num_sms ? ntiles : (size_t)st->num_sms);
+      launch_chained_smem(k, grid, threads, (size_t)smem, st->stream, f + off, st->W + off, st->Z + off, st->ld, len, st->S);
+      st->launches += 1;
+      return;
+    }
+  }
+  const int grid = grid_for(st, per_sm_b(st, u.nz, u.V, len), len, u.V, nka_threads_b(u.nz));
   launch_chained(nka_get_pass_b(u.nz, u.V), grid, nka_threads_b(u.nz), st->stream, f + off, st->W + off, st->Z + off,
                  st->ld, len, st->S);
   st->launches += 1;

@@ -14,3 +14,5 @@ typedef void (*PassBFn)(double*, double*, double*, size_t, size_t, const NkaDevS
 // nc in 1..NKA_MAXSLOT, nz in 0..NKA_MAXSLOT-1, v in {1,2}; nullptr if not instantiated in this build
 PassAFn nka_get_pass_a(int nc, int v);
 PassBFn nka_get_pass_b(int nz, int v);
+// experimental (NKA_PASS_B_TMA=1): operand tiles staged by cp.async.bulk; nullptr if nz is not instantiated
+PassBFn nka_get_pass_b_tma(int nz, int* threads, int* smem_bytes);

@@ -142,20 +142,26 @@ __device__ __forceinline__ double nka_warp_sum(double v)
   return v;
 }
 
-// Programmatic dependent launch (sm_90+).  The kernels of the update chain (pass A -> fix-up ->
-// pass B) are launched with the programmatic-stream-serialization attribute and begin with
-// `griddepcontrol.wait`, which blocks until the previous grid has completed and its memory is
-// visible; nothing is read before it.  Pass A -- the one kernel with a serial tail: ticket, fold,
-// cross-rank exchange, scalar state step, ~24 us on one CTA -- issues `launch_dependents` when its
-// streaming loop is done, so the next kernel's CTAs are scheduled onto the idle SMs during that
-// tail and its launch latency disappears (-6 us per update: 0.320 -> 0.314 ms at n = 2^24, mvec = 5;
-// profiles/r2d_pdl_ab.jsonl).  Only when the kernel that follows is one of ours (fused mode): a
-// library kernel (NCCL) does not wait.  Triggering at the START of every kernel was tried first:
-// the parked CTAs of the dependents then sit beside pass A's streaming CTAs and cost 4-6 %
-// (profiles/r2b_pdl_ab_early_trigger.jsonl), and results were wrong -- not kept.
-// Without the attribute both instructions are no-ops.
+// Programmatic dependent launch (sm_90+) -- EXPERIMENT, compiled in only with -DNKA_EXPERIMENT_PDL
+// and never in the product build.  The kernels of the update chain (pass A -> fix-up -> pass B)
+// were launched with the programmatic-stream-serialization attribute and began with
+// `griddepcontrol.wait`; pass A issued `launch_dependents` when its streaming loop was done, so
+// the next kernel's CTAs were scheduled onto the idle SMs during pass A's serial tail (ticket,
+// fold, exchange, state step: ~24 us on one CTA).  Measured: -6 us per update (0.320 -> 0.314 ms
+// at n = 2^24, mvec = 5; 0.978 -> 0.972 ms at n = 2^25, mvec = 10; profiles/r2d_pdl_ab.jsonl).
+// Triggering at the start of every kernel instead cost 4-6 % (parked CTAs beside the streaming
+// ones, profiles/r2b_pdl_ab_early_trigger.jsonl).  NOT KEPT: with the attribute set, 19 parity
+// tests failed in one full-suite run on small vectors and passed in the next
+// (gpurun_out/pytest_gpu_r2e.log vs bisect_parity_r2f.txt) -- the overlap removes the kernel
+// boundary that the L1-cached (ld.global.nc) loads of W, Z and the device state rely on for
+// coherence, and the loads that avoid L1 cost 10 % of pass B (profiles/r1a_tune_sweep.jsonl).
+#ifdef NKA_EXPERIMENT_PDL
 __device__ __forceinline__ void nka_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void nka_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#else
+__device__ __forceinline__ void nka_pdl_wait() {}
+__device__ __forceinline__ void nka_pdl_trigger() {}
+#endif
 
 __device__ __forceinline__ unsigned long long nka_globaltimer()
 {
@@ -228,6 +234,7 @@ __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* 
     // the same left-to-right sum as a plain loop, with the (independent) loads of eight rows in
     // flight at once: at 1184 rows the plain loop paid 37 L2 round trips per value (16 us)
     unsigned b = lane;
+#ifndef NKA_FOLD_PLAIN
     for (; b + 7 * 32 < fold_rows; b += 8 * 32) {
       double t[8];
 #pragma unroll
@@ -235,6 +242,7 @@ __device__ __forceinline__ bool nka_grid_reduce(const double (&acc)[K], double* 
 #pragma unroll
       for (int u = 0; u < 8; ++u) v += t[u];
     }
+#endif
     for (; b < fold_rows; b += 32) v += __ldcg(&fold_base[(size_t)b * K + j]);
     v = nka_warp_sum(v);
     if (lane == 0) out(j, v);

@@ -101,6 +101,19 @@ def test_scenarios_match_oracle_without_lazy_column(name):
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("name", ["iid_n1000_m10", "picard_n500_m5_v2", "n4097_m2", "collinear_n400_m20",
+                                  "relax_restart_n96_m4"])
+def test_scenarios_match_oracle_with_tma_staged_pass_b(name):
+    """The cp.async.bulk staging experiment (NKA_PASS_B_TMA=1, nka_pass_b_tma.cu) computes the same
+    thing: steady-state plans go through the mbarrier ring, drops / odd n / other sizes through its
+    general body or the regular kernel."""
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r + '/tests'); "
+            "import test_gpu_parity as T; T.test_scenarios_match_oracle(%r); print('ok')" % (ROOT, ROOT, name))
+    env = dict(os.environ, NKA_PASS_B_TMA="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
 @pytest.mark.parametrize("name", ["iid_n64_m3", "iid_n1000_m10", "odd_n1023_m7", "n4097_m2", "mvec1_n17"])
 def test_well_conditioned_strict_1e12(name):
     """Strict bar, no noise allowance: ||got - want|| <= 1e-12 ||want|| on every call."""
