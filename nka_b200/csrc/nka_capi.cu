@@ -507,6 +507,7 @@ static int launch_pass_a(NKA st, const UpdateShape& u, double* f, size_t off, si
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
   NKA_REQUIRE(row0 + grid <= st->max_grid, "pass A: too many partial rows");
   double* rows = st->partials + (size_t)row0 * 2 * u.NC;
+  NkaRange nvtx("nka:pass_a");
   SpanScope t(st, T_PASS_A);
   launch_chained(nka_get_pass_a(u.NC, u.V), grid, NKA_THREADS_A, st->stream,
                  f + off, st->W + off, st->ld, len, st->S, rows, st->ticket, st->dots, u.fused ? 1 : 0, st->peer,
@@ -519,6 +520,7 @@ static int launch_pass_a(NKA st, const UpdateShape& u, double* f, size_t off, si
 // into pass A, the fix-up for the lazily skipped column, or the bare state step of a first call.
 static void launch_mid(NKA st, const UpdateShape& u, double* f)
 {
+  NkaRange nvtx("nka:state");
   const size_t n = st->vlen;
   if (u.L > 0) {
     if (!u.fused) {
@@ -547,6 +549,7 @@ static void launch_mid(NKA st, const UpdateShape& u, double* f)
 
 static void launch_pass_b(NKA st, const UpdateShape& u, double* f, size_t off, size_t len)
 {
+  NkaRange nvtx("nka:pass_b");
   SpanScope t(st, T_PASS_B);
   if (g_pass_b_tma && u.V == 2 && len % 2 == 0 && len > 0) {
     int threads = 0, smem = 0;
@@ -577,6 +580,7 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
   NKA_REQUIRE(st != NULL, "nka_accel_update: null handle");
   NKA_REQUIRE(f != NULL || st->vlen == 0, "nka_accel_update: null vector");
   DeviceGuard guard(st->device);
+  NkaRange nvtx("nka:accel_update");
   const UpdateShape u = update_shape(st, f);
   if (u.L > 0) launch_pass_a(st, u, f, 0, st->vlen, 0, 0, true);
   launch_mid(st, u, f);
@@ -601,6 +605,7 @@ extern "C" void nka_accel_update_host(NKA st, double* f)
   NKA_REQUIRE(st != NULL, "nka_accel_update: null handle");
   NKA_REQUIRE(f != NULL || st->vlen == 0, "nka_accel_update: null vector");
   DeviceGuard guard(st->device);
+  NkaRange nvtx("nka:accel_update(host f: h2d | sweeps | d2h, pipelined)");
   const size_t n = st->vlen;
   const size_t bytes = n * sizeof(double);
   if (!st->fstage) CUDA_CHECK(cudaMalloc(&st->fstage, bytes ? bytes : 16));

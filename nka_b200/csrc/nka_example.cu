@@ -206,7 +206,13 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
 // own partial sum of r^2, folded in item order by the last CTA: run-to-run bit-stable.
 #define EX_RS_COLS 30
 #define EX_RS_THREADS 256
-#define EX_RS_PF 4
+#define EX_RS_WARPS (EX_RS_THREADS / 32)
+#ifndef EX_RS_PF
+#define EX_RS_PF 8               // diagonals in flight per warp (cp.async groups)
+#endif
+#ifndef EX_RS_MINB
+#define EX_RS_MINB 4             // CTAs per SM the register budget is held to
+#endif
 
 struct ResStripParams {
   ResParams p;
@@ -214,8 +220,20 @@ struct ResStripParams {
   unsigned* counter;             // next item
 };
 
-__global__ void __launch_bounds__(EX_RS_THREADS) ex_residual_strip_kernel(ResStripParams Q)
+// 8 bytes global -> shared, asynchronously; nbytes = 0 writes zeros and reads nothing
+__device__ __forceinline__ void ex_cp_async8(double* dst_smem, const double* src, unsigned nbytes)
 {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
+               :: "r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src), "r"(nbytes) : "memory");
+}
+
+__global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_kernel(ResStripParams Q)
+{
+  // operands of the diagonals ahead, per warp: [stage][u | z][lane].  Plain register prefetching does
+  // not work for a walk like this (an in-order warp has six load scoreboards: waiting for the oldest
+  // load also waits for the youngest that shares its scoreboard -- 57 % of the stall samples of the
+  // first version, profiles/r2e_residual_strip_ncu.txt), cp.async groups retire in order instead.
+  __shared__ double ring[EX_RS_WARPS][EX_RS_PF][2][32];
   const ResParams& P = Q.p;
   const int nx = P.nx, ny = P.ny;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -225,6 +243,8 @@ __global__ void __launch_bounds__(EX_RS_THREADS) ex_residual_strip_kernel(ResStr
   const double* __restrict__ HLO = P.HLO;
   const double* __restrict__ HHI = P.HHI;
   const int tmax = nx + ny - 2;                       // last diagonal with cells
+  const int kmin = HLO ? -1 : 0, kmax = HHI ? ny : ny - 1;          // rows that exist, edge rows of the neighbouring slabs included
+  double (*myring)[2][32] = ring[warp];
 
   for (;;) {
     unsigned item = 0;
@@ -233,7 +253,7 @@ __global__ void __launch_bounds__(EX_RS_THREADS) ex_residual_strip_kernel(ResStr
     if (item >= nitems) break;
     const int b = (int)(item / (unsigned)Q.nstrips), s = (int)(item - (unsigned)b * (unsigned)Q.nstrips);
     const int j = s * EX_RS_COLS - 1 + lane;
-    const bool cin = (unsigned)j < (unsigned)nx;
+    const bool cin = (unsigned)j < (unsigned)nx, cinl = (unsigned)(j - 1) < (unsigned)nx;
     const bool mine = lane >= 1 && lane <= EX_RS_COLS && cin;
     const int t0 = s * EX_RS_COLS + b * Q.band;                       // first diagonal this item finishes
     int t1 = t0 + Q.band;                                             // one past the last
@@ -241,8 +261,8 @@ __global__ void __launch_bounds__(EX_RS_THREADS) ex_residual_strip_kernel(ResStr
     if (t1 > tend) t1 = tend;
     if (t1 > tmax + 1) t1 = tmax + 1;
 
-    // what a lane sees at (j, k): in-grid value, a neighbouring slab's edge row, or nothing
-    auto fetch = [&](int tau, long long base, double& ur, double& zr) {
+    // what a lane sees at (j, k): in-grid value, a neighbouring slab's edge row, or nothing (zeros)
+    auto fetch = [&](int tau, long long base, int stage) {
       const int k = tau - j;
       const bool live = cin && tau <= t1;                             // nothing beyond the band's last step
       const bool ing = live && (unsigned)k < (unsigned)ny;
@@ -250,29 +270,25 @@ __global__ void __launch_bounds__(EX_RS_THREADS) ex_residual_strip_kernel(ResStr
       bool pr = ing;
       if (live && k == -1 && HLO) { pu = HLO + j; pr = true; }
       if (live && k == ny && HHI) { pu = HHI + j; pr = true; }
-      ur = pr ? __ldg(pu) : 0.0;
-      zr = (ing && Zc) ? __ldg(Zc + (base + j)) : 0.0;
-    };
-    auto present = [&](int jj, int k) {
-      const bool c = (unsigned)jj < (unsigned)nx;
-      return c && ((unsigned)k < (unsigned)ny || (k == -1 && HLO != nullptr) || (k == ny && HHI != nullptr));
+      ex_cp_async8(&myring[stage][0][lane], pr ? pu : U, pr ? 8u : 0u);
+      if (Zc) ex_cp_async8(&myring[stage][1][lane], ing ? Zc + (base + j) : Zc, ing ? 8u : 0u);
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
     auto next_base = [&](int tau, long long base) -> long long {      // wf_base(tau + 1) from wf_base(tau)
       return (tau >= 0 && tau <= tmax - 1) ? base + wf_step(tau, nx, ny) : 0;
     };
 
-    // prefetch ring
-    double ub[EX_RS_PF], zb[EX_RS_PF];
     int tf = t0 - 1;
     long long basef = (tf >= 0 && tf <= tmax) ? wf_base(tf, nx, ny) : 0;
 #pragma unroll
     for (int i = 0; i < EX_RS_PF; ++i) {
-      fetch(tf, basef, ub[i], zb[i]);
+      fetch(tf, basef, i);
       basef = next_base(tf, basef);
       ++tf;
     }
 
     double u_pp = 0.0, u_p = 0.0, tx_p = 0.0, ty_p = 0.0, fx_p = 1.0, fy_p = 1.0;
+    bool pc_p = false;                                                 // was (j, k-1) there: the previous step's own cell
     long long base_c = (t0 - 1 >= 0 && t0 - 1 <= tmax) ? wf_base(t0 - 1, nx, ny) : 0, base_p = 0;
     double rr = 0.0;
     for (int tau0 = t0 - 1; tau0 <= t1; tau0 += EX_RS_PF) {
@@ -281,16 +297,18 @@ __global__ void __launch_bounds__(EX_RS_THREADS) ex_residual_strip_kernel(ResStr
         const int tau = tau0 + i;
         if (tau <= t1) {                                               // warp-uniform
           const int k = tau - j;
-          const bool pc = present(j, k);
-          const double u_n = Zc ? __dsub_rn(ub[i], zb[i]) : ub[i];    // u = u - r : F08 :248 (z = 0 outside the grid)
-          fetch(tf, basef, ub[i], zb[i]);                              // refill the slot, EX_RS_PF diagonals ahead
+          const bool krange = k >= kmin && k <= kmax;
+          const bool pc = cin && krange, pl = cinl && krange, pd = pc_p;
+          asm volatile("cp.async.wait_group %0;" :: "n"(EX_RS_PF - 1) : "memory");
+          const double ub = myring[i][0][lane];
+          const double u_n = Zc ? __dsub_rn(ub, myring[i][1][lane]) : ub;   // u = u - r : F08 :248 (z = 0 outside the grid)
+          fetch(tf, basef, i);                                         // refill the stage, EX_RS_PF diagonals ahead
           basef = next_base(tf, basef);
           ++tf;
           // update_system (:122-145)
           const double tc = __ddiv_rn(1.0, __dadd_rn(P.a, u_n));
           const double tx_n = __dmul_rn(tc, P.fx), ty_n = __dmul_rn(tc, P.fy);
           const double tx_l = __shfl_up_sync(0xffffffffu, tx_p, 1);    // (j-1, k) sits on diagonal tau-1
-          const bool pl = present(j - 1, k), pd = present(j, k - 1);
           const double sx = (pl && pc) ? __dadd_rn(tx_l, tx_n) : (pl ? tx_l : tx_n);
           const double sy = (pd && pc) ? __dadd_rn(ty_p, ty_n) : (pd ? ty_p : ty_n);
           const double fx_n = __ddiv_rn(2.0, sx);                      // left face of (j, k)
@@ -316,13 +334,14 @@ __global__ void __launch_bounds__(EX_RS_THREADS) ex_residual_strip_kernel(ResStr
             if (kc == ny - 1) P.AYT[j] = ayu;
             rr = __dadd_rn(rr, __dmul_rn(r, r));
           }
-          u_pp = u_p; u_p = pc ? u_n : 0.0;
-          tx_p = tx_n; ty_p = ty_n; fx_p = fx_n; fy_p = fy_n;
+          u_pp = u_p; u_p = u_n;
+          tx_p = tx_n; ty_p = ty_n; fx_p = fx_n; fy_p = fy_n; pc_p = pc;
           base_p = base_c;
           base_c = next_base(tau, base_c);
         }
       }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");               // nothing of this item may land in the next item's ring
     rr = ex_warp_sum(rr);
     if (lane == 0) P.partials[item] = rr;
   }
@@ -913,7 +932,7 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
     sy->rs_strips = (nx + EX_RS_COLS - 1) / EX_RS_COLS;
     const int ndiag = ny + EX_RS_COLS - 1;                             // diagonals a strip has cells on
     const long long warps = (long long)sy->num_sms * occ * (EX_RS_THREADS / 32);
-    int per_warp = 4;                                                  // items per resident warp aimed at
+    int per_warp = 2;                                                  // items per resident warp aimed at
     if (const char* e = getenv("NKA_RES_ITEMS_PER_WARP")) if (atoi(e) > 0) per_warp = atoi(e);
     long long bands = (warps * per_warp + sy->rs_strips - 1) / sy->rs_strips;
     int band = (int)((ndiag + bands - 1) / (bands > 0 ? bands : 1));
@@ -1082,6 +1101,7 @@ extern "C" double nka_system_residual(NKASYS sy, int subtract_z)
 {
   NKA_REQUIRE(sy != NULL, "nka_system_residual: null handle");
   DeviceGuard guard(sy->device);
+  NkaRange nvtx("nka:example residual");
   ResParams P;
   P.nx = sy->nx; P.ny = sy->ny;
   P.U = sy->U[sy->cur];
@@ -1142,6 +1162,7 @@ extern "C" int nka_system_pc_ssor(NKASYS sy, int nsweep, double omega)
   NKA_REQUIRE(nsweep >= 1, "nka_system_pc_ssor: nsweep must be >= 1");       // F08 :156-157
   NKA_REQUIRE(omega > 0.0, "nka_system_pc_ssor: omega must be > 0");
   DeviceGuard guard(sy->device);
+  NkaRange nvtx("nka:example pc_ssor");
   if (sy->bnd_dirty) {
     const size_t nb = (size_t)sy->nstrips * sy->ny;
     ex_fill_u64<<<ex_grid(sy, nb, 256), 256, 0, sy->stream>>>(sy->bnd, nb, EX_SENT);

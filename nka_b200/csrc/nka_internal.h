@@ -5,6 +5,16 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+// NVTX ranges (header-only NVTX3: no link dependency, a no-op unless a profiler is attached):
+// "nka:accel_update" around an update, "nka:pass_a", "nka:state", "nka:pass_b", "nka:h2d/d2h" inside.
+#include <nvtx3/nvToolsExt.h>
+struct NkaRange {
+  explicit NkaRange(const char* name) { nvtxRangePushA(name); }
+  ~NkaRange() { nvtxRangePop(); }
+  NkaRange(const NkaRange&) = delete;
+  NkaRange& operator=(const NkaRange&) = delete;
+};
+
 [[noreturn]] void nka_fail(const char* file, int line, const char* msg);
 
 #define NKA_REQUIRE(cond, msg) do { if (!(cond)) nka_fail(__FILE__, __LINE__, msg); } while (0)

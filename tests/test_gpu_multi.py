@@ -129,6 +129,29 @@ def _example_worker(rank, world, port, case, q):
             out["z2"] = sy.get(FIELD_Z)
             out["rows"] = (sy.k0, sy.k1)
             sy.delete()
+        elif case["kind"] == "steps":
+            # the Picard loop one kernel at a time, every field of every iteration saved for the parent
+            from nka_b200 import _lib
+            lib = _lib.load()
+            nx, ny = case["nx"], case["ny"]
+            sy = distributed_system(0.02, nx, ny, scaling=1, device=rank)
+            so = Solver(sy, nsweep=2, omega=1.4, mvec=case["mvec"], vtol=0.01)
+            save = lambda tag, it, a: np.save(os.path.join(case["dir"], "%s_%d_r%d.npy" % (tag, it, rank)), a)
+            out["rnorm"] = [sy.residual(subtract_z=False)]
+            save("r", 0, sy.get(FIELD_R))
+            out["nvec"] = []
+            for it in range(1, case["iters"] + 1):
+                sy.pc_ssor(2, 1.4)
+                save("zssor", it, sy.get(FIELD_Z))
+                lib.nka_accel_update_dev(so.accel._handle(), sy.field_ptr(FIELD_Z))
+                out["nvec"].append(so.accel.num_vec())
+                save("zacc", it, sy.get(FIELD_Z))
+                out["rnorm"].append(sy.residual(subtract_z=True))
+                save("u", it, sy.get(FIELD_U))
+                save("r", it, sy.get(FIELD_R))
+            out["rows"] = (sy.k0, sy.k1)
+            out["mode"] = so.accel.comm_mode()
+            so.delete(); sy.delete()
         else:
             sy = distributed_system(0.02, case["nx"], case["ny"], scaling=case["scaling"], device=rank)
             so = Solver(sy, nsweep=2, omega=1.4, mvec=case["mvec"], vtol=0.01)
@@ -152,7 +175,7 @@ def _run_example(case, world=2):
     procs = [ctx.Process(target=_example_worker, args=(r, world, port, case, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = dict(q.get(timeout=240) for _ in range(world))
+    got = dict(q.get(timeout=case.get("timeout", 240)) for _ in range(world))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -198,3 +221,58 @@ def test_slab_example_reproduces_golden_tables():
     got = _run_example({"kind": "solve", "nx": 50, "ny": 50, "scaling": 0, "mvec": 0})
     assert got[0]["iters"] == 367
     assert api.format_table(got[0]["rnorm"]) == lines(unacc_txt)
+
+
+def test_all_gpus_8192_picard_steps_against_cpu_oracle(tmp_path_factory):
+    """BASELINE.json configs[3] at a size the CPU oracle still checks: 8192 x 8192 on every GPU of
+    the box (row slabs), three Picard iterations taken one kernel at a time.  Each device kernel is
+    compared with the CPU loops ON THE DEVICE'S OWN INPUT, so the comparison is exact where the
+    reference is order-exact: residual and update_system (np.array_equal on r and u), the
+    slab-pipelined SSOR sweeps across all slab boundaries (np.array_equal on z), accel_update with
+    the cross-rank sum fused into pass A (1e-12 against the long-double arbiter replaying the
+    device's f-sequence, identical num_vec), norms to 1e-9."""
+    import shutil
+    import torch
+    from oracle import api
+    world = torch.cuda.device_count()
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = min(world, 8)
+    nx = ny = 8192
+    iters, mvec = 3, 5
+    d = "/dev/shm/nka_steps_%d" % os.getpid()
+    os.makedirs(d, exist_ok=True)
+    try:
+        got = _run_example({"kind": "steps", "nx": nx, "ny": ny, "iters": iters, "mvec": mvec, "dir": d,
+                            "timeout": 900}, world=world)
+        join = lambda tag, it: np.concatenate([np.load(os.path.join(d, "%s_%d_r%d.npy" % (tag, it, r)), mmap_mode="r")
+                                               for r in range(world)], axis=0)
+        assert all(got[r]["mode"] == "peer" for r in range(world))
+        assert all(got[r]["rnorm"] == got[0]["rnorm"] and got[r]["nvec"] == got[0]["nvec"] for r in range(world))
+        assert [got[r]["rows"] for r in range(world)] == [((ny * r) // world, (ny * (r + 1)) // world) for r in range(world)]
+        orc = api.OracleSystem(nx, ny, 0.02, 1)
+        arb = api.OracleNKA(nx * ny, mvec, 0.01, dotmode=1)
+        pad = np.zeros((ny + 2, nx + 2))
+        r_cpu = orc.residual(pad).reshape(ny, nx)
+        assert np.array_equal(join("r", 0), r_cpu)
+        assert abs(got[0]["rnorm"][0] - orc.norm2(r_cpu.ravel())) <= 1e-9 * got[0]["rnorm"][0]
+        u_prev = np.zeros((ny, nx))
+        for it in range(1, iters + 1):
+            r_dev = join("r", it - 1)
+            z_cpu = orc.pc_ssor(2, 1.4, np.ascontiguousarray(r_dev).ravel()).reshape(ny, nx)
+            z_dev = join("zssor", it)
+            assert np.array_equal(z_dev, z_cpu), ("ssor", it)
+            want = np.ascontiguousarray(z_dev).ravel().copy()
+            arb.accel_update(want)
+            zacc = np.ascontiguousarray(join("zacc", it))
+            assert np.linalg.norm(zacc.ravel() - want) <= 1e-12 * np.linalg.norm(want), ("accel", it)
+            assert got[0]["nvec"][it - 1] == arb.num_vec()
+            u_dev = join("u", it)
+            assert np.array_equal(u_dev, u_prev - zacc), ("u", it)
+            pad[1:-1, 1:-1] = u_dev
+            r_cpu = orc.residual(pad).reshape(ny, nx)
+            assert np.array_equal(join("r", it), r_cpu), ("residual", it)
+            assert abs(got[0]["rnorm"][it] - orc.norm2(r_cpu.ravel())) <= 1e-9 * got[0]["rnorm"][it]
+            u_prev = np.ascontiguousarray(u_dev)
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
