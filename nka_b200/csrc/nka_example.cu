@@ -206,12 +206,11 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
 // own partial sum of r^2, folded in item order by the last CTA: run-to-run bit-stable.
 #define EX_RS_COLS 30
 #define EX_RS_THREADS 256
-#define EX_RS_WARPS (EX_RS_THREADS / 32)
 #ifndef EX_RS_PF
-#define EX_RS_PF 8               // diagonals in flight per warp (cp.async groups)
+#define EX_RS_PF 2               // diagonals per load batch
 #endif
 #ifndef EX_RS_MINB
-#define EX_RS_MINB 4             // CTAs per SM the register budget is held to
+#define EX_RS_MINB 4             // CTAs per SM the register budget is held to (64 registers, 32 B of spills)
 #endif
 
 struct ResStripParams {
@@ -220,20 +219,8 @@ struct ResStripParams {
   unsigned* counter;             // next item
 };
 
-// 8 bytes global -> shared, asynchronously; nbytes = 0 writes zeros and reads nothing
-__device__ __forceinline__ void ex_cp_async8(double* dst_smem, const double* src, unsigned nbytes)
-{
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;"
-               :: "r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src), "r"(nbytes) : "memory");
-}
-
 __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_kernel(ResStripParams Q)
 {
-  // operands of the diagonals ahead, per warp: [stage][u | z][lane].  Plain register prefetching does
-  // not work for a walk like this (an in-order warp has six load scoreboards: waiting for the oldest
-  // load also waits for the youngest that shares its scoreboard -- 57 % of the stall samples of the
-  // first version, profiles/r2e_residual_strip_ncu.txt), cp.async groups retire in order instead.
-  __shared__ double ring[EX_RS_WARPS][EX_RS_PF][2][32];
   const ResParams& P = Q.p;
   const int nx = P.nx, ny = P.ny;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -244,7 +231,6 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
   const double* __restrict__ HHI = P.HHI;
   const int tmax = nx + ny - 2;                       // last diagonal with cells
   const int kmin = HLO ? -1 : 0, kmax = HHI ? ny : ny - 1;          // rows that exist, edge rows of the neighbouring slabs included
-  double (*myring)[2][32] = ring[warp];
 
   for (;;) {
     unsigned item = 0;
@@ -262,7 +248,7 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
     if (t1 > tmax + 1) t1 = tmax + 1;
 
     // what a lane sees at (j, k): in-grid value, a neighbouring slab's edge row, or nothing (zeros)
-    auto fetch = [&](int tau, long long base, int stage) {
+    auto fetch = [&](int tau, long long base, double& ur, double& zr) {
       const int k = tau - j;
       const bool live = cin && tau <= t1;                             // nothing beyond the band's last step
       const bool ing = live && (unsigned)k < (unsigned)ny;
@@ -270,19 +256,25 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
       bool pr = ing;
       if (live && k == -1 && HLO) { pu = HLO + j; pr = true; }
       if (live && k == ny && HHI) { pu = HHI + j; pr = true; }
-      ex_cp_async8(&myring[stage][0][lane], pr ? pu : U, pr ? 8u : 0u);
-      if (Zc) ex_cp_async8(&myring[stage][1][lane], ing ? Zc + (base + j) : Zc, ing ? 8u : 0u);
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      ur = pr ? __ldg(pu) : 0.0;
+      zr = (ing && Zc) ? __ldg(Zc + (base + j)) : 0.0;
     };
     auto next_base = [&](int tau, long long base) -> long long {      // wf_base(tau + 1) from wf_base(tau)
       return (tau >= 0 && tau <= tmax - 1) ? base + wf_step(tau, nx, ny) : 0;
     };
 
+    // Operands are loaded a BATCH of EX_RS_PF diagonals at a time, one batch ahead of use, and handed
+    // over between batches.  (Refilling one register slot per step, EX_RS_PF steps ahead, looks
+    // equivalent but is not: the in-order warp has six load scoreboards, so waiting for the oldest
+    // load also waits for the youngest that shares its scoreboard -- 57 % of the stall samples of
+    // that version, profiles/r2e_residual_strip_ncu.txt.  A cp.async ring instead moved the stalls
+    // to the memory-instruction queue, next to the step's eight shuffles: profiles/r2h_*.)
+    double cu[EX_RS_PF], cz[EX_RS_PF], nu[EX_RS_PF], nz[EX_RS_PF];
     int tf = t0 - 1;
     long long basef = (tf >= 0 && tf <= tmax) ? wf_base(tf, nx, ny) : 0;
 #pragma unroll
     for (int i = 0; i < EX_RS_PF; ++i) {
-      fetch(tf, basef, i);
+      fetch(tf, basef, cu[i], cz[i]);
       basef = next_base(tf, basef);
       ++tf;
     }
@@ -293,18 +285,19 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
     double rr = 0.0;
     for (int tau0 = t0 - 1; tau0 <= t1; tau0 += EX_RS_PF) {
 #pragma unroll
+      for (int i = 0; i < EX_RS_PF; ++i) {                             // the next batch, all loads back to back
+        fetch(tf, basef, nu[i], nz[i]);
+        basef = next_base(tf, basef);
+        ++tf;
+      }
+#pragma unroll
       for (int i = 0; i < EX_RS_PF; ++i) {
         const int tau = tau0 + i;
         if (tau <= t1) {                                               // warp-uniform
           const int k = tau - j;
           const bool krange = k >= kmin && k <= kmax;
           const bool pc = cin && krange, pl = cinl && krange, pd = pc_p;
-          asm volatile("cp.async.wait_group %0;" :: "n"(EX_RS_PF - 1) : "memory");
-          const double ub = myring[i][0][lane];
-          const double u_n = Zc ? __dsub_rn(ub, myring[i][1][lane]) : ub;   // u = u - r : F08 :248 (z = 0 outside the grid)
-          fetch(tf, basef, i);                                         // refill the stage, EX_RS_PF diagonals ahead
-          basef = next_base(tf, basef);
-          ++tf;
+          const double u_n = Zc ? __dsub_rn(cu[i], cz[i]) : cu[i];    // u = u - r : F08 :248 (z = 0 outside the grid)
           // update_system (:122-145)
           const double tc = __ddiv_rn(1.0, __dadd_rn(P.a, u_n));
           const double tx_n = __dmul_rn(tc, P.fx), ty_n = __dmul_rn(tc, P.fy);
@@ -340,8 +333,9 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
           base_c = next_base(tau, base_c);
         }
       }
+#pragma unroll
+      for (int i = 0; i < EX_RS_PF; ++i) { cu[i] = nu[i]; cz[i] = nz[i]; }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");               // nothing of this item may land in the next item's ring
     rr = ex_warp_sum(rr);
     if (lane == 0) P.partials[item] = rr;
   }
@@ -932,7 +926,7 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
     sy->rs_strips = (nx + EX_RS_COLS - 1) / EX_RS_COLS;
     const int ndiag = ny + EX_RS_COLS - 1;                             // diagonals a strip has cells on
     const long long warps = (long long)sy->num_sms * occ * (EX_RS_THREADS / 32);
-    int per_warp = 2;                                                  // items per resident warp aimed at
+    int per_warp = 4;                                                  // items per resident warp aimed at (0.28 vs 0.43 ms with 2 at 4096^2: profiles/r2i_residual_ab.jsonl)
     if (const char* e = getenv("NKA_RES_ITEMS_PER_WARP")) if (atoi(e) > 0) per_warp = atoi(e);
     long long bands = (warps * per_warp + sy->rs_strips - 1) / sy->rs_strips;
     int band = (int)((ndiag + bands - 1) / (bands > 0 ? bands : 1));
