@@ -51,10 +51,16 @@
 #endif
 #define NKA_STATE_THREADS 128
 // Pass B holds NZ column values (double2) and 2 NZ coefficients per thread: beyond 12 columns the
-// 128 registers a 512-thread CTA allows spill (388 B at NZ = 20: 5.9 instead of 7.0 TB/s), so the
-// larger instantiations run 256 threads with up to 255 registers.
+// 128 registers a 512-thread CTA allows spill (388 B at NZ = 20: 5.9 instead of 7.0 TB/s).  From
+// NKA_COEF_SMEM_FROM columns on, the 2 NZ coefficients live in shared memory (one broadcast LDS.64
+// per use: the sweep is HBM bound, the issue slots are free) so that the column values alone fill the
+// registers and the CTA keeps its 512 threads; beyond NKA_THREADS_B_WIDE_FROM columns even those
+// do not fit and the CTA drops to 256 threads with up to 255 registers.
+#ifndef NKA_COEF_SMEM_FROM
+#define NKA_COEF_SMEM_FROM 13
+#endif
 #ifndef NKA_THREADS_B_WIDE_FROM
-#define NKA_THREADS_B_WIDE_FROM 13
+#define NKA_THREADS_B_WIDE_FROM 24
 #endif
 __host__ __device__ constexpr int nka_threads_b(int nz) { return nz >= NKA_THREADS_B_WIDE_FROM ? 256 : NKA_THREADS_B; }
 
@@ -527,14 +533,30 @@ nka_pass_b(double* __restrict__ f, double* W, double* Z, size_t ld, size_t n, co
   double* wnew = W + (size_t)B->newslot * ld;
   double* zp = Z + (size_t)B->pslot * ld;
   const double coef_p = B->coef_p;
-  const double* zcol[NZA];
-  double coefN[NZA], coefY[NZA];
+  constexpr bool kCoefSmem = NZ >= NKA_COEF_SMEM_FROM;    // coefficients and column addresses in shared memory
+  __shared__ double s_coefN[kCoefSmem ? NZA : 1], s_coefY[kCoefSmem ? NZA : 1];
+  __shared__ const double* s_zcol[kCoefSmem ? NZA : 1];
+  double r_coefN[kCoefSmem ? 1 : NZA], r_coefY[kCoefSmem ? 1 : NZA];
+  const double* r_zcol[kCoefSmem ? 1 : NZA];
+  double (&coefN)[NZA] = *reinterpret_cast<double (*)[NZA]>(kCoefSmem ? s_coefN : r_coefN);
+  double (&coefY)[NZA] = *reinterpret_cast<double (*)[NZA]>(kCoefSmem ? s_coefY : r_coefY);
+  const double* (&zcol)[NZA] = *reinterpret_cast<const double* (*)[NZA]>(kCoefSmem ? s_zcol : r_zcol);
+  if (!kCoefSmem) {
 #pragma unroll
-  for (int k = 0; k < NZA; ++k) {
-    const bool on = (k < nz) && (k < NZ);
-    zcol[k] = Z + (size_t)(on ? B->zcol[k] : B->newslot) * ld;
-    coefN[k] = on ? B->coefN[k] : 0.0;
-    coefY[k] = on ? B->coefY[k] : 0.0;
+    for (int k = 0; k < NZA; ++k) {
+      const bool on = (k < nz) && (k < NZ);
+      zcol[k] = Z + (size_t)(on ? B->zcol[k] : B->newslot) * ld;
+      coefN[k] = on ? B->coefN[k] : 0.0;
+      coefY[k] = on ? B->coefY[k] : 0.0;
+    }
+  } else {
+    for (int k = threadIdx.x; k < NZA; k += blockDim.x) {
+      const bool on = (k < nz) && (k < NZ);
+      s_zcol[k] = Z + (size_t)(on ? B->zcol[k] : B->newslot) * ld;
+      s_coefN[k] = on ? B->coefN[k] : 0.0;
+      s_coefY[k] = on ? B->coefY[k] : 0.0;
+    }
+    __syncthreads();
   }
   const size_t nv = n / V;
   const size_t stride = (size_t)gridDim.x * nka_threads_b(NZ);
