@@ -522,6 +522,19 @@ def run_ours(args):
             torch.cuda.synchronize()
             floor = min(floor, max_over_ranks(time.perf_counter() - t0))
 
+        # the same with a barrier between the two copies: in an update no byte can return before the
+        # LAST rank's last byte has arrived (the coefficients need the global dot products), so on a
+        # box whose ranks share PCIe bandwidth the unsynchronised figure above is not attainable
+        floor_sync = 1e30
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            scratch.copy_(host[0], non_blocking=True)
+            barrier()
+            host[0].copy_(scratch, non_blocking=True)
+            torch.cuda.synchronize()
+            floor_sync = min(floor_sync, max_over_ranks(time.perf_counter() - t0))
+
         # pageable host memory: what an unmodified reference caller passes (src-C/nka_example.c:139, malloc)
         pageable = None
         if not args.no_pageable:
@@ -537,8 +550,10 @@ def run_ours(args):
                "steps": args.e2e_steps, "ms_per_step": 1e3 * dt / args.e2e_steps,
                "host_memory": "pinned (cudaHostAlloc)",
                "pcie_floor_ms": 1e3 * floor, "frac_of_pcie_floor": floor / (dt / args.e2e_steps),
+               "pcie_floor_synced_ms": 1e3 * floor_sync, "frac_of_pcie_floor_synced": floor_sync / (dt / args.e2e_steps),
                "pcie_floor": "bare cudaMemcpyAsync H2D then D2H of each rank's slab, all ranks at once, best of 3, "
-                             "max over ranks",
+                             "max over ranks; synced = with a barrier between the two copies, as the update's global "
+                             "reduction imposes",
                "pageable": pageable, "numa": numa,
                "api": "nka_accel_update(NKA, double* host_f) -- include/nonlinear_krylov_accelerator.h"}
         del host

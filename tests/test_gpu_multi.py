@@ -229,11 +229,13 @@ def test_all_gpus_8192_picard_steps_against_cpu_oracle(tmp_path_factory):
     compared with the CPU loops ON THE DEVICE'S OWN INPUT, so the comparison is exact where the
     reference is order-exact: residual and update_system (np.array_equal on r and u), the
     slab-pipelined SSOR sweeps across all slab boundaries (np.array_equal on z), accel_update with
-    the cross-rank sum fused into pass A (1e-12 against the long-double arbiter replaying the
-    device's f-sequence, identical num_vec), norms to 1e-9."""
+    the cross-rank sum fused into pass A (against the long-double arbiter replaying the device's
+    f-sequence: 1e-12, or twice the reference's own serial-vs-long-double spread where that is
+    larger; identical num_vec), norms to 1e-9."""
     import shutil
     import torch
     from oracle import api
+    from parity_log import record_parity
     world = torch.cuda.device_count()
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -252,6 +254,8 @@ def test_all_gpus_8192_picard_steps_against_cpu_oracle(tmp_path_factory):
         assert [got[r]["rows"] for r in range(world)] == [((ny * r) // world, (ny * (r + 1)) // world) for r in range(world)]
         orc = api.OracleSystem(nx, ny, 0.02, 1)
         arb = api.OracleNKA(nx * ny, mvec, 0.01, dotmode=1)
+        ser = api.OracleNKA(nx * ny, mvec, 0.01, dotmode=0)      # the unmodified reference's arithmetic
+        spread = 0.0
         pad = np.zeros((ny + 2, nx + 2))
         r_cpu = orc.residual(pad).reshape(ny, nx)
         assert np.array_equal(join("r", 0), r_cpu)
@@ -264,8 +268,18 @@ def test_all_gpus_8192_picard_steps_against_cpu_oracle(tmp_path_factory):
             assert np.array_equal(z_dev, z_cpu), ("ssor", it)
             want = np.ascontiguousarray(z_dev).ravel().copy()
             arb.accel_update(want)
+            wser = np.ascontiguousarray(z_dev).ravel().copy()
+            ser.accel_update(wser)
             zacc = np.ascontiguousarray(join("zacc", it))
-            assert np.linalg.norm(zacc.ravel() - want) <= 1e-12 * np.linalg.norm(want), ("accel", it)
+            # the example's corrections are nearly parallel (ill-conditioned Gram matrix): the bar is
+            # 1e-12 or the reference's own serial-vs-long-double spread on this very sequence, as in
+            # tests/scenarios.py: tolerances (factor 2)
+            spread = max(spread, np.linalg.norm(wser - want) / np.linalg.norm(want))
+            err = np.linalg.norm(zacc.ravel() - want) / np.linalg.norm(want)
+            record_parity("example_8192_all_gpus_it%d" % it, n=nx * ny, mvec=mvec, vtol=0.01, ranks=world,
+                          err_vs_arbiter=float(err), reference_serial_vs_arbiter=float(spread),
+                          tol_used=float(max(1e-12, 2 * spread)))
+            assert err <= max(1e-12, 2 * spread), ("accel", it, err, spread)
             assert got[0]["nvec"][it - 1] == arb.num_vec()
             u_dev = join("u", it)
             assert np.array_equal(u_dev, u_prev - zacc), ("u", it)
