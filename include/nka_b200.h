@@ -41,6 +41,13 @@ int nka_defined (NKA);
 
 size_t nka_vec_len64 (NKA);
 
+/* src-F08/nka_type.F90:209-219 (set_dot_prod), and the per-call `dp` of src-F95/nka_type.F90:284-291:
+ * install (or with dp == NULL remove) the global-sum callback after construction; see
+ * nonlinear_krylov_accelerator.h for how dp is used.  The _ctx form passes a caller context
+ * through (what a Fortran trampoline needs to find its procedure pointer). */
+void nka_set_dot_prod (NKA, double (*dp)(int, double *, double *));
+void nka_set_dot_prod_ctx (NKA, double (*dp)(int, double *, double *, void *), void *ctx);
+
 /* ---- the hot path with explicit memory spaces -------------------------- */
 
 /* f is a device pointer on the handle's device; asynchronous on the handle's

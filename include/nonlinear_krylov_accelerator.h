@@ -11,10 +11,14 @@
  *   - `f` passed to nka_accel_update may be a DEVICE pointer (zero copy, the
  *     intended use: iterates never cross PCIe) or a HOST pointer (staged
  *     host->device->host inside the call, synchronous, for drop-in use);
- *   - `dp` must be NULL.  A host dot-product callback cannot be called from a
- *     kernel; the global reduction the hook exists for
- *     (src-C/...c:61-68) is built in: see nka_comm_init in nka_b200.h.
- *     A non-NULL dp aborts with a message (never a silent wrong answer).
+ *   - `dp` (src-C/...c:61-68, :227-231): NULL = the built-in reductions (one GPU, or
+ *     all ranks of nka_comm_init in nka_b200.h).  A non-NULL dp is honoured as what the
+ *     reference documents it for -- the GLOBAL sum in a parallel run: the device forms this
+ *     process's partial dot products over its portion of the vectors, and each partial p is
+ *     made global by calling dp(1, &p, &one) on the host (p times 1.0, summed over the
+ *     processes by the caller's own reduction).  The n-long vectors are never handed to dp:
+ *     it must be a plain Euclidean dot product followed by a sum over processes.  This path
+ *     costs one device->host->device round trip per update (the 2*(mvec+1) scalars).
  *   - violated preconditions and CUDA failures print "file:line: message" on
  *     stderr and abort(), the reference's ASSERT convention
  *     (src-C/...c:217-219, src-F08/f90_assert.F90:37-47).

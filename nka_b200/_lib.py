@@ -41,6 +41,8 @@ SYMBOLS = {
     # include/nka_b200.h
     "nka_init_ex": (C.c_void_p, [C.c_size_t, C.c_int, C.c_double, C.c_int, C.c_void_p]),
     "nka_set_vec_tol": (None, [C.c_void_p, C.c_double]),
+    "nka_set_dot_prod": (None, [C.c_void_p, C.c_void_p]),
+    "nka_set_dot_prod_ctx": (None, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "nka_defined": (C.c_int, [C.c_void_p]),
     "nka_vec_len64": (C.c_size_t, [C.c_void_p]),
     "nka_accel_update_dev": (None, [C.c_void_p, C.c_void_p]),

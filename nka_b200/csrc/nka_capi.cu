@@ -149,6 +149,11 @@ struct nka_state {
   bool pending = false;
   int ub_len = 0;
   bool lazy = true;             // skip the doomed oldest column in pass A (single GPU only)
+  // the reference's dp hook: global sum of each partial dot product through a host callback
+  double (*dp)(int, double*, double*) = nullptr;
+  double (*dp_ctx)(int, double*, double*, void*) = nullptr;
+  void* dp_user = nullptr;
+  double* dots_host = nullptr;  // pinned, 2*NKA_MAXSLOT
   // distributed
   NkaComm* comm = nullptr;
   // peer-memory reduction fused into pass A (all ranks on one NVLink domain); else NCCL
@@ -445,13 +450,37 @@ static void set_lazy(NKA st, bool on)
   st->launches += 1;
 }
 
+static void install_dp(NKA st, double (*dp)(int, double*, double*), double (*dp_ctx)(int, double*, double*, void*), void* user)
+{
+  NKA_REQUIRE(st->comm == nullptr || (!dp && !dp_ctx),
+              "nka_set_dot_prod: the handle already sums over ranks through nka_comm_init; use one or the other");
+  DeviceGuard guard(st->device);
+  st->dp = dp; st->dp_ctx = dp_ctx; st->dp_user = user;
+  // the lazily skipped oldest column would need a second, conditional reduction: not with a host callback
+  bool lazy = !(dp || dp_ctx);
+  if (lazy) if (const char* e = getenv("NKA_LAZY_LAST")) lazy = atoi(e) != 0;
+  set_lazy(st, lazy);
+}
+
+extern "C" void nka_set_dot_prod(NKA st, double (*dp)(int, double*, double*))
+{
+  NKA_REQUIRE(st != NULL, "nka_set_dot_prod: null handle");
+  install_dp(st, dp, nullptr, nullptr);
+}
+
+extern "C" void nka_set_dot_prod_ctx(NKA st, double (*dp)(int, double*, double*, void*), void* ctx)
+{
+  NKA_REQUIRE(st != NULL, "nka_set_dot_prod_ctx: null handle");
+  install_dp(st, nullptr, dp, ctx);
+}
+
 extern "C" NKA nka_init(int vlen, int mvec, double vtol, double (*dp)(int, double*, double*))
 {
+  // src-C/nonlinear_krylov_accelerator.c:211-258; dp: :227-231 (NULL selects the built-in reductions)
   NKA_REQUIRE(vlen >= 0, "nka_init: vlen must be >= 0");
-  NKA_REQUIRE(dp == NULL,
-              "nka_init: a host dot-product callback cannot run inside a CUDA kernel; pass NULL and use "
-              "nka_comm_init for a global (multi-GPU) reduction");
-  return nka_init_ex((size_t)vlen, mvec, vtol, -1, NULL);
+  NKA st = nka_init_ex((size_t)vlen, mvec, vtol, -1, NULL);
+  if (dp) install_dp(st, dp, nullptr, nullptr);
+  return st;
 }
 
 extern "C" void nka_delete(NKA st)
@@ -465,6 +494,7 @@ extern "C" void nka_delete(NKA st)
   nka_comm_release(st->comm);
   cudaFree(st->W); cudaFree(st->Z); cudaFree(st->S); cudaFree(st->dots);
   cudaFree(st->partials); cudaFree(st->ticket); cudaFree(st->fstage);
+  if (st->dots_host) cudaFreeHost(st->dots_host);
   if (st->copy_in) {
     cudaStreamDestroy(st->copy_in); cudaStreamDestroy(st->copy_out);
     for (cudaEvent_t ev : st->chunk_ev) cudaEventDestroy(ev);
@@ -492,7 +522,7 @@ static UpdateShape update_shape(NKA st, const double* f)
   u.L = st->ub_len;                               // upper bound on the list length at entry
   // fused = the dot products are complete when pass A's last CTA has them (single GPU, or
   // summed over the ranks through peer memory inside pass A): state step in place, lazy last column
-  u.fused = (st->comm == nullptr) || (st->peer != nullptr);
+  u.fused = ((st->comm == nullptr) || (st->peer != nullptr)) && !st->dp && !st->dp_ctx;
   u.may_skip = u.fused && st->lazy && st->pending && u.L == st->mvec + 1;
   u.NC = u.may_skip ? st->mvec : u.L;             // columns pass A can be asked to stream
   u.nz = nz_expected(st);
@@ -523,7 +553,27 @@ static void launch_mid(NKA st, const UpdateShape& u, double* f)
   NkaRange nvtx("nka:state");
   const size_t n = st->vlen;
   if (u.L > 0) {
-    if (!u.fused) {
+    if (!u.fused && (st->dp || st->dp_ctx)) {
+      // the caller's reduction: every partial dot product becomes global through dp(1, &p, &1.0)
+      {
+        SpanScope t(st, T_COMM);
+        const size_t bytes = 2 * NKA_MAXSLOT * sizeof(double);
+        if (!st->dots_host) CUDA_CHECK(cudaMallocHost(&st->dots_host, bytes));
+        CUDA_CHECK(cudaMemcpyAsync(st->dots_host, st->dots, bytes, cudaMemcpyDeviceToHost, st->stream));
+        CUDA_CHECK(cudaStreamSynchronize(st->stream));
+        double one = 1.0;
+        for (int half = 0; half < 2; ++half)
+          for (int j = 0; j < u.L; ++j) {
+            double* p = st->dots_host + half * NKA_MAXSLOT + j;
+            double part = *p;
+            *p = st->dp ? st->dp(1, &part, &one) : st->dp_ctx(1, &part, &one, st->dp_user);
+          }
+        CUDA_CHECK(cudaMemcpyAsync(st->dots, st->dots_host, bytes, cudaMemcpyHostToDevice, st->stream));
+      }
+      SpanScope t(st, T_STATE);
+      launch_chained(nka_state_kernel, 1, NKA_STATE_THREADS, st->stream, st->S, st->dots, 1);
+      st->launches += 1;
+    } else if (!u.fused) {
       {
         SpanScope t(st, T_COMM);
         const int rc = g_nccl.AllReduce(st->dots, st->dots, 2 * NKA_MAXSLOT, kNcclFloat64, kNcclSum, st->comm->comm, st->stream);
@@ -836,6 +886,7 @@ extern "C" int nka_comm_unique_id(void* id128)
 
 static void attach_comm(NKA st, NkaComm* c)
 {
+  NKA_REQUIRE(!st->dp && !st->dp_ctx, "nka_comm_init: the handle already reduces through a dp callback; use one or the other");
   peer_teardown(st);
   nka_comm_release(st->comm);
   st->comm = c;

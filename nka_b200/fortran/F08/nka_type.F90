@@ -13,9 +13,11 @@
 !!   call this%accel_update(f_dev)            additive: type(c_ptr) device address, asynchronous
 !!   call this%relax() / this%restart()       :439-457 / :422-436
 !!
-!! set_dot_prod (:209-214) is kept for source compatibility but a host procedure cannot be
-!! called from a kernel: it stops with a message.  The distributed dot product it exists for
-!! is built into the library (nka_comm_init).
+!! set_dot_prod (:209-214) installs the caller's dot product as what the reference documents
+!! it for, the GLOBAL sum of a parallel run: the device forms this process's partial dot
+!! products and each partial p becomes global as dot_prod([p], [1.0]) -- so dot_prod must be a
+!! Euclidean dot product followed by a sum over the processes (include/
+!! nonlinear_krylov_accelerator.h).  comm_init is the built-in alternative (NVLink / NCCL).
 !!
 !! NOT COMPILED in the build image (no Fortran compiler); see nka_b200_c.F90.
 !!
@@ -28,9 +30,14 @@ module nka_type
   implicit none
   private
 
+  type :: dp_holder
+    procedure(dp), pointer, nopass :: f => null()
+  end type dp_holder
+
   type, public :: nka
     private
     type(c_ptr) :: handle = c_null_ptr
+    type(dp_holder), pointer :: hook => null()   ! heap cell: its address is the callback's context
   contains
     procedure :: init
     procedure :: set_vec_tol
@@ -70,12 +77,14 @@ contains
     class(nka), intent(inout) :: this
     if (c_associated(this%handle)) call nka_delete_c(this%handle)
     this%handle = c_null_ptr
+    if (associated(this%hook)) deallocate(this%hook)
   end subroutine
 
   subroutine nka_final(this)
     type(nka), intent(inout) :: this
     if (c_associated(this%handle)) call nka_delete_c(this%handle)
     this%handle = c_null_ptr
+    if (associated(this%hook)) deallocate(this%hook)
   end subroutine
 
   subroutine set_vec_tol(this, vtol)
@@ -87,9 +96,26 @@ contains
   subroutine set_dot_prod(this, dot_prod)
     class(nka), intent(inout) :: this
     procedure(dp), pointer :: dot_prod
-    write(error_unit,'(a)') 'nka%set_dot_prod: a host dot product cannot run on the device; use nka%comm_init'
-    error stop 1
+    if (.not.associated(dot_prod)) then          ! ASSERT(associated(dot_prod)), src-F08/nka_type.F90:212
+      write(error_unit,'(a)') 'nka%set_dot_prod: dot_prod is not associated'
+      error stop 1
+    end if
+    if (.not.associated(this%hook)) allocate(this%hook)
+    this%hook%f => dot_prod
+    call nka_set_dot_prod_ctx(this%handle, c_funloc(dp_trampoline), c_loc(this%hook))
   end subroutine
+
+  !! What the library calls (double (*)(int, double *, double *, void *)): finds the user's
+  !! procedure pointer through ctx and hands it the two n-vectors as assumed-shape arrays.
+  function dp_trampoline(n, x, y, ctx) bind(C) result(s)
+    integer(c_int), value :: n
+    real(c_double), intent(in) :: x(n), y(n)
+    type(c_ptr), value :: ctx
+    real(c_double) :: s
+    type(dp_holder), pointer :: hook
+    call c_f_pointer(ctx, hook)
+    s = hook%f(x, y)
+  end function
 
   !! Collective over the ranks that each own a slab of every vector (one process per GPU).
   subroutine comm_init(this, nranks, rank, id128)

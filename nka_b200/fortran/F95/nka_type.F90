@@ -13,9 +13,10 @@
 !!   call nka_delete (this)                    :266-275
 !!   nka_num_vec, nka_max_vec, nka_vec_len, nka_vec_tol, nka_real_kind, nka_defined
 !!
-!! Differences, all forced by the device: a user dot product `dp` cannot run inside a kernel
-!! and is rejected (the global reduction it exists for is built in: nka_comm_init); the
-!! default vtol (0.01, :194) is passed at creation.  Preconditions keep the reference's
+!! Differences, all forced by the device: a user dot product `dp` is used for what the
+!! reference documents it for, the global sum of a parallel run -- each partial dot product p
+!! of this process's portion becomes global as dp([p], [1.0]) (include/
+!! nonlinear_krylov_accelerator.h); the default vtol (0.01, :194) is passed at creation.  Preconditions keep the reference's
 !! ASSERT semantics (checked in the C library: message with file:line, then abort).
 !!
 !! NOT COMPILED in the build image (no Fortran compiler); see nka_b200_c.F90.
@@ -42,6 +43,17 @@ module nka_type
   interface nka_accel_update
     module procedure nka_accel_update_host_array, nka_accel_update_device
   end interface
+
+  abstract interface
+    pure function dp_iface (x, y)
+      import :: r8
+      real(r8), intent(in) :: x(:), y(:)
+      real(r8) :: dp_iface
+    end function dp_iface
+  end interface
+  !! the dp of the nka_accel_update call in progress (the call is synchronous; not thread-safe,
+  !! as little as the reference's module is)
+  procedure(dp_iface), pointer, save :: current_dp => null()
 
 contains
 
@@ -109,8 +121,8 @@ contains
     optional :: dp
     real(r8), allocatable :: tmp(:)
     if (present(dp)) then
-      write(0,'(a)') 'nka_accel_update: a user dot product cannot run on the device; use nka_comm_init'
-      stop 1
+      current_dp => dp
+      call nka_set_dot_prod_ctx (this%handle, c_funloc(dp_trampoline), c_null_ptr)
     end if
     if (is_contiguous(f)) then
       call nka_accel_update_host (this%handle, f)
@@ -119,7 +131,21 @@ contains
       call nka_accel_update_host (this%handle, tmp)
       f = tmp
     end if
+    if (present(dp)) then
+      call nka_set_dot_prod_ctx (this%handle, c_null_funptr, c_null_ptr)
+      current_dp => null()
+    end if
   end subroutine nka_accel_update_host_array
+
+  !! What the library calls (double (*)(int, double *, double *, void *)) while an update with a
+  !! per-call dp is in progress.
+  function dp_trampoline (n, x, y, ctx) bind(C) result(s)
+    integer(c_int), value :: n
+    real(c_double), intent(in) :: x(n), y(n)
+    type(c_ptr), value :: ctx
+    real(c_double) :: s
+    s = current_dp (x, y)
+  end function dp_trampoline
 
   subroutine nka_accel_update_device (this, f_dev)
     type(nka), intent(inout) :: this

@@ -102,6 +102,16 @@ module nka_b200_c
       real(c_double), value :: vtol
     end subroutine
 
+    !! void nka_set_dot_prod_ctx (NKA, double (*dp)(int, double *, double *, void *), void *ctx)
+    !! dp = c_funloc of a bind(C) trampoline, ctx = whatever it needs to find the user's procedure
+    !! pointer; c_null_funptr restores the built-in reductions.
+    subroutine nka_set_dot_prod_ctx(handle, dp, ctx) bind(C, name='nka_set_dot_prod_ctx')
+      import :: c_ptr, c_funptr
+      type(c_ptr), value :: handle
+      type(c_funptr), value :: dp
+      type(c_ptr), value :: ctx
+    end subroutine
+
     function nka_defined_c(handle) bind(C, name='nka_defined') result(ok)
       import :: c_ptr, c_int
       type(c_ptr), value :: handle

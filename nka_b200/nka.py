@@ -96,6 +96,13 @@ class NKA:
     def relax(self): self._lib.nka_relax(self._handle())
     def restart(self): self._lib.nka_restart(self._handle())
 
+    def set_dot_prod(self, dp) -> None:
+        """set_dot_prod(dot_prod): src-F08/nka_type.F90:209-219.  dp(n, x, y) is a ctypes callback of the
+        C header's type (double (*)(int, double*, double*)) or None; the library calls it with n = 1 to
+        make each of this process's partial dot products global (include/nonlinear_krylov_accelerator.h)."""
+        self._dp_keepalive = dp
+        self._lib.nka_set_dot_prod(self._handle(), C.cast(dp, C.c_void_p) if dp is not None else None)
+
     def set_vec_tol(self, vtol: float):
         if not vtol > 0.0:
             raise ValueError("vtol must be > 0")
@@ -161,10 +168,15 @@ def comm_unique_id() -> bytes:
 
 
 # ---- the C header's call shapes (src-C/nonlinear_krylov_accelerator.h:3-12) ----
+DP_FUNC = C.CFUNCTYPE(C.c_double, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double))
+
+
 def nka_init(vlen: int, mvec: int, vtol: float, dp=None) -> NKA:
+    """dp: None, or a DP_FUNC callback (the reference's parallel dot-product hook, used for its global sum)."""
+    acc = NKA(vlen, mvec, vtol)
     if dp is not None:
-        raise ValueError("dp must be None: a host dot product cannot run in a kernel (use comm_init)")
-    return NKA(vlen, mvec, vtol)
+        acc.set_dot_prod(dp)
+    return acc
 
 
 def nka_delete(state: NKA): state.delete()

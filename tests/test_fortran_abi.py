@@ -61,10 +61,10 @@ def test_scalars_by_value_arrays_by_address():
     """A C `double`/`int`/`size_t`/handle parameter must be `value` in Fortran; a `double *` array
     or the 128-byte id must not be."""
     ifaces = _fortran_interfaces()
-    decls = _c_declarations()
+    decls = _c_typed_declarations()                 # parameters split on top-level commas only
     for name, info in ifaces.items():
-        for farg, cparam in zip(info["args"], decls[name]["params"]):
-            is_array = ("double *" in cparam and "NKA" not in cparam) or "id128" in cparam
+        for farg, cparam in zip(info["args"], decls[name]["params_raw"]):
+            is_array = ("double *" in cparam and "NKA" not in cparam and "(*" not in cparam) or "id128" in cparam
             if name in ("nka_accel_update_dev",) and "f_dev" in farg:
                 is_array = False          # device address travels by value in a type(c_ptr)
             assert (farg in info["by_value"]) == (not is_array), (name, farg, cparam)
@@ -247,8 +247,8 @@ def test_fortran_binding_shim_compiles_against_the_headers(tmp_path):
             if not raw_is_pointer:
                 return "void *"                        # Fortran passes an address, the header wants a scalar: must not compile
             t = re.sub(r"\[[^\]]*\]", "", raw)
-            if "(*" in t:
-                return "double (*)(int, double *, double *)"
+            if "(*" in t:                             # function pointer: the header's own type, name removed
+                return re.sub(r"\(\*\s*\w+\)", "(*)", t)
             words = t.replace("*", " * ").split()
             if words[-1] != "*" and words[-1] not in _HANDLES and len(words) > 1:
                 words = words[:-1]

@@ -9,7 +9,7 @@ Which oracle: the serial-sum port (bit-identical to the compiled reference)
 for n <= 2^18; above that the same algorithm with long-double dot products,
 because the reference's own left-to-right summation noise exceeds 1e-12 there
 (hard part 3).  For the deliberately ill-conditioned stress
-sequences the tolerance is the larger of 1e-12 and 10x the reference's own
+sequences the tolerance is the larger of 1e-12 and 4x the reference's own
 serial-vs-long-double spread (tests/scenarios.py: tolerances).
 """
 import os
@@ -43,7 +43,7 @@ def _rel(a, b):
 
 @pytest.mark.parametrize("name", sorted(S.SCENARIOS))
 def test_scenarios_match_oracle(name):
-    """Decisions identical on every call; corrections within max(1e-12, 10x the reference's own
+    """Decisions identical on every call; corrections within max(1e-12, 4x the reference's own
     serial-vs-long-double spread) of the long-double arbiter (S.tolerances)."""
     from nka_b200 import NKA
     n, mvec, vtol, mk = S.SCENARIOS[name]
@@ -55,7 +55,7 @@ def test_scenarios_match_oracle(name):
     orc = api.OracleNKA(n, mvec, vtol, dotmode=0)
     acc = NKA(n, mvec, vtol)
     it = 0
-    worst_arb = worst_ser = 0.0
+    worst_arb = worst_ser = worst_ratio = 0.0
     ndrops = 0
     for op in ops:
         if op[0] == "update":
@@ -73,6 +73,8 @@ def test_scenarios_match_oracle(name):
             err = np.linalg.norm(got - arbiter[it]) / scales[it]
             worst_arb = max(worst_arb, err)
             worst_ser = max(worst_ser, np.linalg.norm(got - serial[it]) / scales[it])
+            if err > 1e-12:        # only where the relaxed bar is in play: err / (the reference's spread so far)
+                worst_ratio = max(worst_ratio, err / (tols[it] / 4.0))
             assert err <= tols[it], (name, it, err, tols[it])
             it += 1
         elif op[0] == "relax":
@@ -86,7 +88,7 @@ def test_scenarios_match_oracle(name):
     record_parity(name, n=n, mvec=mvec, vtol=vtol, calls=it, drops=ndrops,
                   err_vs_arbiter=worst_arb, err_vs_serial_reference=worst_ser,
                   reference_serial_vs_arbiter=spread, tol_used=max(tols),
-                  fraction_of_tol_used=worst_arb / max(tols))
+                  fraction_of_tol_used=worst_arb / max(tols), worst_ratio_to_reference_spread=worst_ratio)
 
 
 @pytest.mark.parametrize("name", ["fullthendrop_n700_m32", "fullthendrop_n300_m4", "picard_n500_m5_v2",
@@ -212,6 +214,50 @@ def test_host_pointer_path_large_pinned_matches_device_path():
         assert float((got - f).norm() / f.norm()) <= 1e-13, t
         assert a.num_vec() == b.num_vec()
     a.delete(); b.delete()
+
+
+@pytest.mark.parametrize("name", ["iid_n1000_m10", "picard_n500_m5_v2", "relax_restart_n96_m4", "repeats_n128_m4"])
+def test_dot_product_hook_is_used_for_the_global_sum(name):
+    """nka_init(vlen, mvec, vtol, dp) with a non-NULL dp (src-C/...c:227-231): each partial dot product
+    of the device goes through dp(1, &p, &one) -- here a one-process "global sum", so the results
+    must equal the built-in path's; the call count shows the hook really carries every dot."""
+    import ctypes as C
+    from nka_b200 import _lib
+    from nka_b200.nka import DP_FUNC
+    lib = _lib.load()
+    n, mvec, vtol, mk = S.SCENARIOS[name]
+    ops = mk()
+    inputs = [op[1] for op in ops if op[0] == "update"]
+    serial, _ = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=0), ops)
+    arbiter, nv = S.run_ops(api.OracleNKA(n, mvec, vtol, dotmode=1), ops)
+    scales, tols = S.tolerances(serial, arbiter, inputs)
+    calls = []
+
+    def dp(m, x, y):
+        calls.append(m)
+        return x[0] * y[0]
+    cb = DP_FUNC(dp)
+    h = lib.nka_init(n, mvec, vtol, C.cast(cb, C.c_void_p))
+    it = 0
+    for k, op in enumerate(ops):
+        if op[0] == "update":
+            got = op[1].copy()
+            lib.nka_accel_update(h, got.ctypes.data)
+            assert np.linalg.norm(got - arbiter[it]) / scales[it] <= tols[it], (name, it)
+            it += 1
+        elif op[0] == "relax":
+            lib.nka_relax(h)
+        else:
+            lib.nka_restart(h)
+        assert lib.nka_num_vec(h) == nv[k], (name, k)
+    assert lib.nka_defined(h)
+    assert len(calls) >= 2 * (it - 2) and set(calls) == {1}       # two dots per list position per update, n = 1 each
+    lib.nka_set_dot_prod(h, None)                                  # back to the built-in reduction
+    ncalls = len(calls)
+    f = inputs[0].copy()
+    lib.nka_accel_update(h, f.ctypes.data)
+    assert len(calls) == ncalls
+    lib.nka_delete(h)
 
 
 def test_device_pointer_autodetected_by_drop_in_entry():
