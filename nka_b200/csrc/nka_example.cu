@@ -765,6 +765,7 @@ __global__ void __launch_bounds__(64) ex_ssor_sweep(SsorParams P)
 }
 
 #include "nka_ssor2.cuh"
+#include "nka_ssor3.cuh"
 
 // ex_ssor_sweep2 is compiled per direction x {trace off, on} x {one GPU, row slabs}
 template <typename F>
@@ -785,6 +786,28 @@ static void ex2_launch(int grid, cudaStream_t stream, const SsorParams& P, bool 
   } else {
     if (slabs) ex_ssor_sweep2<DIR, false, true><<<grid, EX2_THREADS, EX2_SMEM_BYTES, stream>>>(P);
     else ex_ssor_sweep2<DIR, false, false><<<grid, EX2_THREADS, EX2_SMEM_BYTES, stream>>>(P);
+  }
+}
+
+// ex_ssor_sweep3: the same variants
+template <typename F>
+static void ex3_for_each_variant(F f)
+{
+  f(ex_ssor_sweep3<1, false, false>); f(ex_ssor_sweep3<-1, false, false>);
+  f(ex_ssor_sweep3<1, false, true>);  f(ex_ssor_sweep3<-1, false, true>);
+  f(ex_ssor_sweep3<1, true, false>);  f(ex_ssor_sweep3<-1, true, false>);
+  f(ex_ssor_sweep3<1, true, true>);   f(ex_ssor_sweep3<-1, true, true>);
+}
+
+template <int DIR>
+static void ex3_launch(int grid, cudaStream_t stream, const SsorParams& P, bool slabs)
+{
+  if (P.trace) {
+    if (slabs) ex_ssor_sweep3<DIR, true, true><<<grid, EX3_THREADS, EX3_SMEM_BYTES, stream>>>(P);
+    else ex_ssor_sweep3<DIR, true, false><<<grid, EX3_THREADS, EX3_SMEM_BYTES, stream>>>(P);
+  } else {
+    if (slabs) ex_ssor_sweep3<DIR, false, true><<<grid, EX3_THREADS, EX3_SMEM_BYTES, stream>>>(P);
+    else ex_ssor_sweep3<DIR, false, false><<<grid, EX3_THREADS, EX3_SMEM_BYTES, stream>>>(P);
   }
 }
 
@@ -824,7 +847,7 @@ struct nka_system {
   int rs_grid = 0, rs_strips = 0, rs_bands = 0, rs_band = 0;
   unsigned* rs_counter = nullptr;
   int ssor_grid = 0;
-  int ssor_kernel = 2;             // 2: ex_ssor_sweep2 (the chain on a warp of its own); 1: ex_ssor_sweep (NKA_SSOR_KERNEL=1, kept for A/B timing)
+  int ssor_kernel = 2;             // 2: ex_ssor_sweep2 (the chain on a warp of its own); 3: ex_ssor_sweep3 (two columns, two chains per lane); 1: ex_ssor_sweep (A/B timing)
   bool bnd_dirty = true;
   int error = 0;
   unsigned long long launches = 0;
@@ -903,7 +926,11 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
   }
   CUDA_CHECK(cudaMalloc(&sy->AXR, ny * sizeof(double)));
   CUDA_CHECK(cudaMalloc(&sy->AYT, nx * sizeof(double)));
-  sy->nstrips = (nx + 31) / 32;
+  const char* kv = getenv("NKA_SSOR_KERNEL");
+  sy->ssor_kernel = kv ? atoi(kv) : 2;
+  NKA_REQUIRE(sy->ssor_kernel >= 1 && sy->ssor_kernel <= 3, "NKA_SSOR_KERNEL must be 1, 2 or 3");
+  const int strip_cols = sy->ssor_kernel == 3 ? EX3_W : 32;
+  sy->nstrips = (nx + strip_cols - 1) / strip_cols;
   CUDA_CHECK(cudaMalloc(&sy->bnd, (size_t)sy->nstrips * ny * sizeof(unsigned long long)));
   {
     const size_t nitems = (size_t)(nx + ny - 1) * (((nx < ny ? nx : ny) + EX_RES_THREADS - 1) / EX_RES_THREADS);
@@ -949,11 +976,16 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
   CUDA_CHECK(cudaMalloc(&sy->result, 2 * sizeof(double)));
   CUDA_CHECK(cudaMemsetAsync(sy->result, 0, 2 * sizeof(double), sy->stream));
   CUDA_CHECK(cudaMallocHost(&sy->result_host, 2 * sizeof(double)));
-  const char* kv = getenv("NKA_SSOR_KERNEL");
-  sy->ssor_kernel = kv ? atoi(kv) : 2;
-  NKA_REQUIRE(sy->ssor_kernel == 1 || sy->ssor_kernel == 2, "NKA_SSOR_KERNEL must be 1 or 2");
   int occ = 0, occb = 0;
-  if (sy->ssor_kernel == 2) {
+  if (sy->ssor_kernel == 3) {
+    occ = occb = 1 << 20;
+    ex3_for_each_variant([&occ](auto kernel) {
+      CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EX3_SMEM_BYTES));
+      int o = 0;
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, kernel, EX3_THREADS, EX3_SMEM_BYTES));
+      if (o < occ) occ = o;
+    });
+  } else if (sy->ssor_kernel == 2) {
     // the grid must be co-resident whichever variant is launched: the smallest occupancy counts
     occ = occb = 1 << 20;
     ex2_for_each_variant([&occ](auto kernel) {
@@ -1184,12 +1216,14 @@ extern "C" int nka_system_pc_ssor(NKASYS sy, int nsweep, double omega)
   for (int i = 0; i < nsweep; ++i) {
     P.zero_old = (i == 0) ? 1 : 0;                       // z = 0 start (:158): nothing to read yet
     P.tag_prev = sy->sweep_id; P.tag_cur = ++sy->sweep_id;
-    if (sy->ssor_kernel == 2) ex2_launch<1>(sy->ssor_grid, sy->stream, P, slabs);
+    if (sy->ssor_kernel == 3) ex3_launch<1>(sy->ssor_grid, sy->stream, P, slabs);
+    else if (sy->ssor_kernel == 2) ex2_launch<1>(sy->ssor_grid, sy->stream, P, slabs);
     else ex_ssor_sweep<1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     P.zero_old = 0;
     P.tag_prev = sy->sweep_id; P.tag_cur = ++sy->sweep_id;
-    if (sy->ssor_kernel == 2) ex2_launch<-1>(sy->ssor_grid, sy->stream, P, slabs);
+    if (sy->ssor_kernel == 3) ex3_launch<-1>(sy->ssor_grid, sy->stream, P, slabs);
+    else if (sy->ssor_kernel == 2) ex2_launch<-1>(sy->ssor_grid, sy->stream, P, slabs);
     else ex_ssor_sweep<-1><<<sy->ssor_grid, 64, 0, sy->stream>>>(P);
     CUDA_CHECK(cudaGetLastError());
     sy->launches += 2;

@@ -31,10 +31,11 @@ def _random_u(nx, ny, seed):
     return rng.uniform(0.0, 0.3, (ny, nx))          # a + u stays positive
 
 
-@pytest.fixture(params=[1, 2], ids=["sweep1", "sweep2"])
+@pytest.fixture(params=[1, 2, 3], ids=["sweep1", "sweep2", "sweep3"])
 def ssor_kernel(request, monkeypatch):
-    """Both SSOR kernels (NKA_SSOR_KERNEL is read when a System is created): ex_ssor_sweep and
-    ex_ssor_sweep2 (the dependent chain on a warp of its own)."""
+    """All SSOR kernels (NKA_SSOR_KERNEL is read when a System is created): ex_ssor_sweep,
+    ex_ssor_sweep2 (the dependent chain on a warp of its own) and ex_ssor_sweep3 (two columns and
+    two independent chains per lane, 64-column strips)."""
     monkeypatch.setenv("NKA_SSOR_KERNEL", str(request.param))
     return request.param
 
@@ -49,6 +50,8 @@ def test_ssor_division_identical():
 
 
 SHAPES = [(3, 3), (5, 4), (4, 9), (31, 17), (32, 32), (33, 70), (50, 50), (96, 40), (257, 129), (300, 300), (700, 64)]
+# strip-edge cases of the 64-column strips of ex_ssor_sweep3: one column into a strip, one short of it, exactly full
+SSOR_SHAPES = SHAPES + [(63, 5), (64, 40), (65, 33), (127, 12), (129, 70)]
 
 
 @pytest.mark.parametrize("nx,ny", SHAPES)
@@ -71,7 +74,7 @@ def test_residual_and_coefficients_bit_identical(nx, ny, scaling):
     sy.delete()
 
 
-@pytest.mark.parametrize("nx,ny", SHAPES)
+@pytest.mark.parametrize("nx,ny", SSOR_SHAPES)
 @pytest.mark.parametrize("nsweep", [1, 2, 3])
 def test_pc_ssor_bit_identical_to_serial_gauss_seidel(nx, ny, nsweep, ssor_kernel):
     from nka_b200.example import System, FIELD_U, FIELD_R, FIELD_Z
@@ -91,12 +94,13 @@ def test_pc_ssor_bit_identical_to_serial_gauss_seidel(nx, ny, nsweep, ssor_kerne
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("nx,ny", [(9700, 7), (40000, 5)])
+@pytest.mark.parametrize("nx,ny", [(9700, 7), (40000, 5), (9601, 6)])
 def test_pc_ssor_more_strips_than_resident_ctas(nx, ny, ssor_kernel):
     """Grids wider than 32 x (resident CTAs): every CTA then walks several strips in turn (the
     32768-wide slab configuration does), so the hand-over barriers, mailbox and edge channels
     must come back idle after each strip.  9700 columns = 304 strips > the 296 resident CTAs of
-    ex_ssor_sweep2; 40000 columns = 1250 strips > ex_ssor_sweep's residency too."""
+    ex_ssor_sweep2 (and 152 strips of 64 > the 148 of ex_ssor_sweep3); 40000 columns = 1250 strips >
+    ex_ssor_sweep's residency too; 9601 = 150 full strips of 64 and one column."""
     from nka_b200.example import System, FIELD_U, FIELD_Z
     u = _random_u(nx, ny, 4242)
     sy = System(0.02, nx, ny, scaling=1)

@@ -25,7 +25,7 @@ steps_t = buf[ns * 4:].astype(np.int64)
 t0 = tr[:, 0].min()
 start, first, end, waits = tr[:, 0] - t0, tr[:, 1] - t0, tr[:, 2] - t0, tr[:, 3]
 order = np.argsort(first + (first <= 0) * 10**15)
-steps = N + 31
+steps = N + (63 if int(__import__("os").environ.get("NKA_SSOR_KERNEL", "2")) == 3 else 31)
 out = {"N": N, "nstrips": int(ns), "sweep_us": float((end.max()) / 1e3),
        "strip_walk_us_median": float(np.median(end - np.maximum(first, start)) / 1e3),
        "ns_per_step_in_walk_median": float(np.median(end - np.maximum(first, start)) / steps),
