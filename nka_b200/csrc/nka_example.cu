@@ -216,6 +216,12 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
 struct ResStripParams {
   ResParams p;
   int nstrips, nbands, band;     // strips of 30 columns; bands of `band` diagonals per strip
+  int absolute;                  // 1: a band is the same range of grid diagonals in every strip (neighbouring strips, handed out
+                                 //    one after the other, then write the sectors they share at about the same time); 0: each
+                                 //    strip's own diagonals cut into bands (equal work per item)
+  unsigned nitems;               // absolute: the (band, strip) pairs that hold cells, numbered band by band
+  const unsigned* first_item;    // absolute: [nbands + 1] number of the first item of each band
+  const int* first_strip;        // absolute: [nbands] first strip with cells in each band
   unsigned* counter;             // next item
 };
 
@@ -224,7 +230,7 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
   const ResParams& P = Q.p;
   const int nx = P.nx, ny = P.ny;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned nitems = (unsigned)Q.nstrips * (unsigned)Q.nbands;
+  const unsigned nitems = Q.absolute ? Q.nitems : (unsigned)Q.nstrips * (unsigned)Q.nbands;
   const double* __restrict__ U = P.U;
   const double* __restrict__ Zc = P.Zc;
   const double* __restrict__ HLO = P.HLO;
@@ -237,15 +243,33 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
     if (lane == 0) item = atomicAdd(Q.counter, 1u);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= nitems) break;
-    const int b = (int)(item / (unsigned)Q.nstrips), s = (int)(item - (unsigned)b * (unsigned)Q.nstrips);
+    int b, s;
+    if (Q.absolute) {
+      // band of this item: the last b with first_item[b] <= item (binary search, warp-uniform)
+      int lo = 0, hi = Q.nbands - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(Q.first_item + mid) <= item) lo = mid; else hi = mid - 1;
+      }
+      b = lo;
+      s = __ldg(Q.first_strip + b) + (int)(item - __ldg(Q.first_item + b));
+    } else {
+      b = (int)(item / (unsigned)Q.nstrips);
+      s = (int)(item - (unsigned)b * (unsigned)Q.nstrips);
+    }
     const int j = s * EX_RS_COLS - 1 + lane;
     const bool cin = (unsigned)j < (unsigned)nx, cinl = (unsigned)(j - 1) < (unsigned)nx;
     const bool mine = lane >= 1 && lane <= EX_RS_COLS && cin;
-    const int t0 = s * EX_RS_COLS + b * Q.band;                       // first diagonal this item finishes
+    int t0 = Q.absolute ? b * Q.band : s * EX_RS_COLS + b * Q.band;   // first diagonal this item finishes
     int t1 = t0 + Q.band;                                             // one past the last
     const int tend = s * EX_RS_COLS + EX_RS_COLS - 1 + ny;            // one past the strip's last diagonal with cells
+    if (t0 < s * EX_RS_COLS) t0 = s * EX_RS_COLS;                     // (absolute bands: the strip starts later / ends earlier)
     if (t1 > tend) t1 = tend;
     if (t1 > tmax + 1) t1 = tmax + 1;
+    if (t0 >= t1) {                                                   // no cell of this strip in the band
+      if (lane == 0) P.partials[item] = 0.0;
+      continue;
+    }
 
     // what a lane sees at (j, k): in-grid value, a neighbouring slab's edge row, or nothing (zeros)
     auto fetch = [&](int tau, long long base, double& ur, double& zr) {
@@ -844,8 +868,11 @@ struct nka_system {
   double* stage = nullptr;         // device scratch for the order conversions
   int res_grid = 0;                // residual kernel: resident CTAs walking (diagonal, chunk) items
   int res_kernel = 2;              // 2: ex_residual_strip_kernel (3 divisions per cell); 1: ex_residual_kernel (NKA_RESIDUAL_KERNEL=1, A/B)
-  int rs_grid = 0, rs_strips = 0, rs_bands = 0, rs_band = 0;
+  int rs_grid = 0, rs_strips = 0, rs_bands = 0, rs_band = 0, rs_absolute = 1;
+  unsigned rs_items = 0;
   unsigned* rs_counter = nullptr;
+  unsigned* rs_first_item = nullptr;   // device: [rs_bands + 1]
+  int* rs_first_strip = nullptr;       // device: [rs_bands]
   int ssor_grid = 0;
   int ssor_kernel = 2;             // 2: ex_ssor_sweep2 (the chain on a warp of its own); 3: ex_ssor_sweep3 (two columns, two chains per lane); 1: ex_ssor_sweep (A/B timing)
   bool bnd_dirty = true;
@@ -960,8 +987,33 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
     if (band < 32) band = 32;                                          // two prologue diagonals per band: <= 6 % redone
     if (const char* e = getenv("NKA_RES_BAND")) if (atoi(e) > 0) band = atoi(e);
     sy->rs_band = band;
-    sy->rs_bands = (ndiag + band - 1) / band;
-    const size_t items = (size_t)sy->rs_strips * sy->rs_bands;
+    sy->rs_absolute = 1;
+    if (const char* e = getenv("NKA_RES_ABS_BANDS")) sy->rs_absolute = atoi(e) != 0;    // A/B switch
+    sy->rs_bands = ((sy->rs_absolute ? nx + ny - 1 : ndiag) + band - 1) / band;
+    size_t items = (size_t)sy->rs_strips * sy->rs_bands;
+    if (sy->rs_absolute) {
+      // (band, strip) pairs that hold cells: strip s has cells on diagonals [30 s, 30 s + 29 + ny), band b is [b B, (b+1) B)
+      std::vector<unsigned> first(sy->rs_bands + 1);
+      std::vector<int> s_lo(sy->rs_bands);
+      size_t count = 0;
+      for (int b = 0; b < sy->rs_bands; ++b) {
+        const long long lo_t = (long long)b * band, hi_t = lo_t + band;           // [lo_t, hi_t)
+        long long s0 = lo_t - (EX_RS_COLS - 1) - ny;                                // 30 s > s0  <=>  the strip has not ended before the band
+        s0 = s0 < 0 ? 0 : s0 / EX_RS_COLS + 1;
+        long long s1 = (hi_t - 1) / EX_RS_COLS;                                     // 30 s <= hi_t - 1  <=>  the strip has started by the band's end
+        if (s1 > sy->rs_strips - 1) s1 = sy->rs_strips - 1;
+        first[b] = (unsigned)count;
+        s_lo[b] = (int)s0;
+        if (s1 >= s0) count += (size_t)(s1 - s0 + 1);
+      }
+      first[sy->rs_bands] = (unsigned)count;
+      items = count;
+      sy->rs_items = (unsigned)count;
+      CUDA_CHECK(cudaMalloc(&sy->rs_first_item, first.size() * sizeof(unsigned)));
+      CUDA_CHECK(cudaMalloc(&sy->rs_first_strip, s_lo.size() * sizeof(int)));
+      CUDA_CHECK(cudaMemcpy(sy->rs_first_item, first.data(), first.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+      CUDA_CHECK(cudaMemcpy(sy->rs_first_strip, s_lo.data(), s_lo.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
     NKA_REQUIRE(items < ((size_t)1 << 31), "nka_system_init: grid too large");
     const size_t ctas = (items + EX_RS_THREADS / 32 - 1) / (EX_RS_THREADS / 32);
     const size_t cap = (size_t)sy->num_sms * occ;
@@ -1018,6 +1070,7 @@ extern "C" void nka_system_delete(NKASYS sy)
   if (sy->comm) { nka_ipc_unmap(sy->comm, sy->zbox_mapped); nka_comm_release(sy->comm); }
   cudaFree(sy->zbox); cudaFree(sy->halo_u_lo); cudaFree(sy->halo_u_hi); cudaFree(sy->send_lo); cudaFree(sy->send_hi);
   cudaFree(sy->partials); cudaFree(sy->ticket); cudaFree(sy->result); cudaFree(sy->stage); cudaFree(sy->rs_counter);
+  cudaFree(sy->rs_first_item); cudaFree(sy->rs_first_strip);
   cudaFreeHost(sy->result_host);
   delete sy;
 }
@@ -1160,7 +1213,8 @@ extern "C" double nka_system_residual(NKASYS sy, int subtract_z)
     ExScope t(sy, 1);
     if (sy->res_kernel == 2) {
       ResStripParams Q;
-      Q.p = P; Q.nstrips = sy->rs_strips; Q.nbands = sy->rs_bands; Q.band = sy->rs_band; Q.counter = sy->rs_counter;
+      Q.p = P; Q.nstrips = sy->rs_strips; Q.nbands = sy->rs_bands; Q.band = sy->rs_band; Q.absolute = sy->rs_absolute; Q.counter = sy->rs_counter;
+      Q.nitems = sy->rs_items; Q.first_item = sy->rs_first_item; Q.first_strip = sy->rs_first_strip;
       ex_residual_strip_kernel<<<sy->rs_grid, EX_RS_THREADS, 0, sy->stream>>>(Q);
     } else {
       ex_residual_kernel<<<sy->res_grid, EX_RES_THREADS, 0, sy->stream>>>(P);
