@@ -980,15 +980,18 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
     sy->rs_strips = (nx + EX_RS_COLS - 1) / EX_RS_COLS;
     const int ndiag = ny + EX_RS_COLS - 1;                             // diagonals a strip has cells on
     const long long warps = (long long)sy->num_sms * occ * (EX_RS_THREADS / 32);
-    int per_warp = 4;                                                  // items per resident warp aimed at (0.28 vs 0.43 ms with 2 at 4096^2: profiles/r2i_residual_ab.jsonl)
+    sy->rs_absolute = 1;
+    if (const char* e = getenv("NKA_RES_ABS_BANDS")) sy->rs_absolute = atoi(e) != 0;    // A/B switch
+    int per_warp = 4;                                                  // per-strip bands: items per resident warp aimed at
     if (const char* e = getenv("NKA_RES_ITEMS_PER_WARP")) if (atoi(e) > 0) per_warp = atoi(e);
     long long bands = (warps * per_warp + sy->rs_strips - 1) / sy->rs_strips;
     int band = (int)((ndiag + bands - 1) / (bands > 0 ? bands : 1));
     if (band < 32) band = 32;                                          // two prologue diagonals per band: <= 6 % redone
+    // absolute bands: 32 diagonals whatever the grid (0.248 ms at 4096^2, 0.927 at 8192^2, 1.87 at 32768 x 4096;
+    // 24 / 48 / 64 are within a few per cent either way, larger bands lose: profiles/r2t_residual_band_sweep.jsonl)
+    if (sy->rs_absolute) band = 32;
     if (const char* e = getenv("NKA_RES_BAND")) if (atoi(e) > 0) band = atoi(e);
     sy->rs_band = band;
-    sy->rs_absolute = 1;
-    if (const char* e = getenv("NKA_RES_ABS_BANDS")) sy->rs_absolute = atoi(e) != 0;    // A/B switch
     sy->rs_bands = ((sy->rs_absolute ? nx + ny - 1 : ndiag) + band - 1) / band;
     size_t items = (size_t)sy->rs_strips * sy->rs_bands;
     if (sy->rs_absolute) {
