@@ -362,7 +362,7 @@ def mvec_sweep(n, pool, gen, stream, peak, torch):
         acc = NKA(n, m, VTOL, stream=stream.cuda_stream)
         k = 0
         with torch.cuda.stream(stream):
-            for _ in range(m + 5):
+            for _ in range(2 * m + 10):         # fill the subspace, then settle: the first ~20 updates on fresh allocations run up to 8 % slow
                 acc.accel_update(pool[k % (m + 3)]); k += 1
         torch.cuda.synchronize()
         steps = 10
