@@ -586,6 +586,7 @@ def run_ours(args):
         ms_b = kb["ms"] / max(kb["count"], 1)
         ms_a = ka["ms"] / max(ka["count"], 1)
         traffic = None
+        traffic_how = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             try:
@@ -593,11 +594,20 @@ def run_ours(args):
                     tj = json.load(fh)
                 key = "n%d_m%d_g%d" % (n, m, world)
                 traffic = tj.get(key, {}).get("pass_b")
+                traffic_how = "ncu --set full capture of this configuration (profiles/traffic.json)"
+                if traffic is None:
+                    # no capture of this rank count (ncu is a one-GPU tool here): the same kernel streams the same
+                    # columns over the rank's slab, so the one-GPU capture scales with the slab length
+                    one = tj.get("n%d_m%d_g1" % (n, m), {}).get("pass_b")
+                    if one is not None:
+                        traffic = one * (n_local / n)
+                        traffic_how = "one-GPU ncu capture scaled by n_local / n (no ncu capture at %d ranks)" % world
             except Exception:
                 traffic = None
         roofline = {"bound": "hbm", "kernel": "nka_pass_b<%d,2>" % m,
                     "achieved": algo_b / (ms_b * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                     "frac": algo_b / (ms_b * 1e-3) / 1e9 / peak, "traffic": traffic,
+                    "traffic_source": traffic_how if traffic is not None else None,
                     "peak_kind": "of " + peak_kind, "algorithmic_bytes_per_launch": algo_b,
                     "avg_launch_ms": ms_b, "launches_timed": kb["count"]}
         line = {

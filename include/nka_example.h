@@ -77,7 +77,14 @@ double nka_system_residual (NKASYS, int subtract_z);
 /* pc_ssor(nsweep, omega, r) (src-F08/nka_example.F90:147-179): z <- nsweep symmetric sweeps
  * of SSOR on A z = r from z = 0, forward then backward, in the reference's lexicographic
  * order and with its operation order (bit-identical to the serial loops).  Asynchronous.
- * Returns 0, or nonzero if a previous sweep on this system reported an internal error. */
+ * Returns 0, or nonzero if a PREVIOUS sweep on this system reported an internal error: the sweeps
+ * are only queued here, so the status of THIS call's sweeps (1 = a strip waited longer than its
+ * time limit for its upstream strip, 2 = for the neighbouring rank's edge row) is picked up by the
+ * next nka_system_residual, which synchronises and reads the device's error word -- as
+ * nka_example_solve does every iteration.  The sweep kernels wait on each other across CTAs: their
+ * grid is sized to be co-resident (occupancy x SMs); a device shared with other work (another
+ * process, MPS, a concurrent kernel of the caller's) can break that, and the symptom is this time-out
+ * (~2 s on one GPU, ~2 min across GPUs), not a hang. */
 int nka_system_pc_ssor (NKASYS, int nsweep, double omega);
 
 /* solver%solve (src-F08/nka_example.F90:226-256): Picard iteration from the current u;

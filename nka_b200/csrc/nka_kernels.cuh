@@ -478,7 +478,7 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
 // element, before W[newslot] is overwritten, so no cross-thread hazard exists).
 // ---------------------------------------------------------------------------
 template <int NZ, int V, bool FULL>
-__device__ __forceinline__ void nka_pass_b_elem(double* __restrict__ f, double* __restrict__ wnew, double* __restrict__ zp,
+__device__ __forceinline__ void nka_pass_b_elem(double* f, double* wnew, double* zp,
                                                 const double* const (&zcol)[NZ > 0 ? NZ : 1],
                                                 const double (&coefN)[NZ > 0 ? NZ : 1],
                                                 const double (&coefY)[NZ > 0 ? NZ : 1], double coef_p,
@@ -486,7 +486,9 @@ __device__ __forceinline__ void nka_pass_b_elem(double* __restrict__ f, double* 
                                                 double* W, const double* Z, size_t ld, const NkaDevState* S)
 {
   using T = Vec<V>;
-  const T x0 = T::ld(f, i);
+  // f is stored to below and wnew / zp point into the W / Z pools: no read-only (ld.global.nc) path and no
+  // restrict promise for them -- PTX defines .nc only for data no thread writes during the kernel
+  const T x0 = T::ld_plain(f, i);
   T zs[NZ > 0 ? NZ : 1];
 #pragma unroll
   for (int k = 0; k < NZ; ++k) {
@@ -524,7 +526,7 @@ __device__ __forceinline__ void nka_pass_b_elem(double* __restrict__ f, double* 
 
 template <int NZ, int V>
 __global__ void __launch_bounds__(nka_threads_b(NZ), NKA_MINB_B)
-nka_pass_b(double* __restrict__ f, double* W, double* Z, size_t ld, size_t n, const NkaDevState* __restrict__ S)
+nka_pass_b(double* f, double* W, double* Z, size_t ld, size_t n, const NkaDevState* __restrict__ S)
 {
   constexpr int NZA = NZ > 0 ? NZ : 1;
   nka_pdl_wait();
