@@ -18,6 +18,7 @@
 #include "nka_internal.h"
 #include "nka_dispatch.h"
 #include "nka_aux_kernels.cuh"
+#include "nka_hostcopy.h"
 
 #define NKA_VERSION "nka_b200 0.1 (sm_100a)"
 
@@ -144,6 +145,10 @@ struct nka_state {
   cudaEvent_t chunk_ev[16] = {};
   cudaEvent_t order_ev = nullptr;
   size_t host_chunk_bytes = 0;
+  // pageable host callers: pinned staging slots the host threads copy through (lazy)
+  double* hslot[3] = {nullptr, nullptr, nullptr};
+  size_t hslot_bytes = 0;
+  cudaEvent_t hslot_ev[3] = {};
   int max_grid = 0;
   // host-side knowledge of the device list: exact `pending`, upper bound on its length
   bool pending = false;
@@ -495,6 +500,10 @@ extern "C" void nka_delete(NKA st)
   cudaFree(st->W); cudaFree(st->Z); cudaFree(st->S); cudaFree(st->dots);
   cudaFree(st->partials); cudaFree(st->ticket); cudaFree(st->fstage);
   if (st->dots_host) cudaFreeHost(st->dots_host);
+  for (int i = 0; i < 3; ++i) {
+    if (st->hslot[i]) cudaFreeHost(st->hslot[i]);
+    if (st->hslot_ev[i]) cudaEventDestroy(st->hslot_ev[i]);
+  }
   if (st->copy_in) {
     cudaStreamDestroy(st->copy_in); cudaStreamDestroy(st->copy_out);
     for (cudaEvent_t ev : st->chunk_ev) cudaEventDestroy(ev);
@@ -650,6 +659,30 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
 #endif
 #define NKA_HOST_MAX_CHUNKS 16
 
+// Host threads for pageable callers (nka_hostcopy.h).  NKA_HOST_THREADS: helpers besides the calling
+// thread (default: up to 7, a quarter of the cores; 0 = leave pageable memory to the driver's own staging).
+static NkaHostCopier* host_copier()
+{
+  static NkaHostCopier* c = nullptr;
+  static bool decided = false;
+  if (!decided) {
+    decided = true;
+    int nt = (int)std::thread::hardware_concurrency() / 4;
+    if (nt > 7) nt = 7;
+    if (nt < 1) nt = 1;
+    if (const char* e = getenv("NKA_HOST_THREADS")) nt = atoi(e);
+    if (nt > 0) c = new NkaHostCopier(nt);           // lives until the process ends
+  }
+  return c;
+}
+
+static bool host_pointer_is_pageable(const void* p)
+{
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return true; }
+  return attr.type == cudaMemoryTypeUnregistered;
+}
+
 extern "C" void nka_accel_update_host(NKA st, double* f)
 {
   NKA_REQUIRE(st != NULL, "nka_accel_update: null handle");
@@ -687,6 +720,21 @@ extern "C" void nka_accel_update_host(NKA st, double* f)
 
   double* d = st->fstage;
   const UpdateShape u = update_shape(st, d);
+  // Pageable caller memory: the host threads copy each chunk into / out of a pinned slot (three slots,
+  // so a slot is refilled while the previous two are on the bus); page-locked memory goes straight to the DMA engines.
+  NkaHostCopier* hc = host_pointer_is_pageable(f) ? host_copier() : nullptr;
+  constexpr int NS = 3;
+  if (hc) {
+    const size_t need = per * sizeof(double);
+    if (st->hslot_bytes < need) {
+      for (int i = 0; i < NS; ++i) {
+        if (st->hslot[i]) CUDA_CHECK(cudaFreeHost(st->hslot[i]));
+        CUDA_CHECK(cudaMallocHost(&st->hslot[i], need));
+        if (!st->hslot_ev[i]) CUDA_CHECK(cudaEventCreateWithFlags(&st->hslot_ev[i], cudaEventDisableTiming));
+      }
+      st->hslot_bytes = need;
+    }
+  }
   // the staging buffer is free once everything queued on the handle's stream has run
   CUDA_CHECK(cudaEventRecord(st->order_ev, st->stream));
   CUDA_CHECK(cudaStreamWaitEvent(st->copy_in, st->order_ev, 0));
@@ -694,19 +742,39 @@ extern "C" void nka_accel_update_host(NKA st, double* f)
   int row0 = 0;
   for (int c = 0; c < nc; ++c) {
     const size_t len = off[c + 1] - off[c];
-    CUDA_CHECK(cudaMemcpyAsync(d + off[c], f + off[c], len * sizeof(double), cudaMemcpyHostToDevice, st->copy_in));
+    const double* src = f + off[c];
+    if (hc) {
+      const int sl = c % NS;
+      if (c >= NS) CUDA_CHECK(cudaEventSynchronize(st->hslot_ev[sl]));      // the slot's previous copy has left it
+      hc->copy(st->hslot[sl], src, len * sizeof(double));
+      src = st->hslot[sl];
+    }
+    CUDA_CHECK(cudaMemcpyAsync(d + off[c], src, len * sizeof(double), cudaMemcpyHostToDevice, st->copy_in));
+    if (hc) CUDA_CHECK(cudaEventRecord(st->hslot_ev[c % NS], st->copy_in));
     CUDA_CHECK(cudaEventRecord(st->chunk_ev[c], st->copy_in));
     CUDA_CHECK(cudaStreamWaitEvent(st->stream, st->chunk_ev[c], 0));
     if (u.L > 0) row0 += launch_pass_a(st, u, d, off[c], len, grid_cap, row0, c == nc - 1);
   }
   launch_mid(st, u, d);
+  // (every copy-in has completed on the device timeline before the first pass B chunk: the slots are free again)
+  auto drain = [&](int c) {                            // chunk c has arrived in its slot: hand it to the caller
+    CUDA_CHECK(cudaEventSynchronize(st->hslot_ev[c % NS]));
+    hc->copy(f + off[c], st->hslot[c % NS], (off[c + 1] - off[c]) * sizeof(double));
+  };
   for (int c = 0; c < nc; ++c) {
     const size_t len = off[c + 1] - off[c];
     launch_pass_b(st, u, d, off[c], len);
     CUDA_CHECK(cudaEventRecord(st->chunk_ev[c], st->stream));
     CUDA_CHECK(cudaStreamWaitEvent(st->copy_out, st->chunk_ev[c], 0));
-    CUDA_CHECK(cudaMemcpyAsync(f + off[c], d + off[c], len * sizeof(double), cudaMemcpyDeviceToHost, st->copy_out));
+    if (hc) {
+      if (c >= NS) drain(c - NS);                     // frees the slot chunk c is about to use
+      CUDA_CHECK(cudaMemcpyAsync(st->hslot[c % NS], d + off[c], len * sizeof(double), cudaMemcpyDeviceToHost, st->copy_out));
+      CUDA_CHECK(cudaEventRecord(st->hslot_ev[c % NS], st->copy_out));
+    } else {
+      CUDA_CHECK(cudaMemcpyAsync(f + off[c], d + off[c], len * sizeof(double), cudaMemcpyDeviceToHost, st->copy_out));
+    }
   }
+  if (hc) for (int c = nc > NS ? nc - NS : 0; c < nc; ++c) drain(c);
   update_done(st, u);
   // later work on the handle's stream must not overtake the copy-out (it may reuse the staging buffer)
   CUDA_CHECK(cudaEventRecord(st->order_ev, st->copy_out));

@@ -477,8 +477,16 @@ nka_pass_a(const double* __restrict__ f, const double* __restrict__ W, size_t ld
 // pair, and the chain-break conversions W[dst] -= W[sub] (same thread, same
 // element, before W[newslot] is overwritten, so no cross-thread hazard exists).
 // ---------------------------------------------------------------------------
+// In the FULL body f, W[newslot], Z[pslot] and the streamed Z columns are distinct arrays: the no-alias promise
+// is true there and lets the compiler lift the next element's loads above this element's stores (worth 8 %
+// at mvec = 2, where an element has only three loads in flight).  The general body reads columns of W that
+// it also writes (the chain-break conversions): no promise.
+template <bool FULL> struct NkaOutPtr { typedef double* type; };
+template <> struct NkaOutPtr<true> { typedef double* __restrict__ type; };
+
 template <int NZ, int V, bool FULL>
-__device__ __forceinline__ void nka_pass_b_elem(double* f, double* wnew, double* zp,
+__device__ __forceinline__ void nka_pass_b_elem(const Vec<V> x0, typename NkaOutPtr<FULL>::type f,
+                                                typename NkaOutPtr<FULL>::type wnew, typename NkaOutPtr<FULL>::type zp,
                                                 const double* const (&zcol)[NZ > 0 ? NZ : 1],
                                                 const double (&coefN)[NZ > 0 ? NZ : 1],
                                                 const double (&coefY)[NZ > 0 ? NZ : 1], double coef_p,
@@ -486,9 +494,8 @@ __device__ __forceinline__ void nka_pass_b_elem(double* f, double* wnew, double*
                                                 double* W, const double* Z, size_t ld, const NkaDevState* S)
 {
   using T = Vec<V>;
-  // f is stored to below and wnew / zp point into the W / Z pools: no read-only (ld.global.nc) path and no
-  // restrict promise for them -- PTX defines .nc only for data no thread writes during the kernel
-  const T x0 = T::ld_plain(f, i);
+  // x0 = f[i], loaded by the caller with a plain load: f is stored to below, and PTX defines the read-only
+  // (ld.global.nc) path only for data that no thread writes during the kernel
   T zs[NZ > 0 ? NZ : 1];
 #pragma unroll
   for (int k = 0; k < NZ; ++k) {
@@ -565,12 +572,22 @@ nka_pass_b(double* f, double* W, double* Z, size_t ld, size_t n, const NkaDevSta
   const size_t start = (size_t)blockIdx.x * nka_threads_b(NZ) + threadIdx.x;
   const bool full = (nz == NZ) && has_pair && write_f && (S->planM.n == 0);
   if (full) {
-    for (size_t i = start; i < nv; i += stride)
-      nka_pass_b_elem<NZ, V, true>(f, wnew, zp, zcol, coefN, coefY, coef_p, has_pair, nz, write_f, i, W, Z, ld, S);
+    // f of the next element is fetched before this element's stores are issued: the compiler cannot lift a
+    // plain load of f above stores to f by itself (it cannot prove i + stride != i), and at small NZ the
+    // loads in flight per thread are what the bandwidth hangs on
+    Vec<V> x0 = start < nv ? Vec<V>::ld_plain(f, start) : Vec<V>::zero();
+    for (size_t i = start; i < nv; i += stride) {
+      const size_t inext = i + stride;
+      const Vec<V> x0n = inext < nv ? Vec<V>::ld_plain(f, inext) : Vec<V>::zero();
+      nka_pass_b_elem<NZ, V, true>(x0, f, wnew, zp, zcol, coefN, coefY, coef_p, has_pair, nz, write_f, i, W, Z, ld, S);
+      x0 = x0n;
+    }
   } else {
     for (size_t i = start; i < nv; i += stride)
-      nka_pass_b_elem<NZ, V, false>(f, wnew, zp, zcol, coefN, coefY, coef_p, has_pair, nz, write_f, i, W, Z, ld, S);
+      nka_pass_b_elem<NZ, V, false>(Vec<V>::ld_plain(f, i), f, wnew, zp, zcol, coefN, coefY, coef_p, has_pair, nz, write_f,
+                                    i, W, Z, ld, S);
   }
   if (V == 2 && (n & 1) && start == 0)
-    nka_pass_b_elem<NZ, 1, false>(f, wnew, zp, zcol, coefN, coefY, coef_p, has_pair, nz, write_f, n - 1, W, Z, ld, S);
+    nka_pass_b_elem<NZ, 1, false>(Vec<1>::ld_plain(f, n - 1), f, wnew, zp, zcol, coefN, coefY, coef_p, has_pair, nz, write_f,
+                                  n - 1, W, Z, ld, S);
 }

@@ -95,7 +95,7 @@ nka_pass_b_tma(double* __restrict__ f, double* W, double* Z, size_t ld, size_t n
     double* wnew_g = W + (size_t)B->newslot * ld;
     double* zp_g = Z + (size_t)B->pslot * ld;
     for (size_t i = (size_t)blockIdx.x * NKA_TMA_CONSUMERS + threadIdx.x; i < n / 2; i += (size_t)gridDim.x * NKA_TMA_CONSUMERS)
-      nka_pass_b_elem<NZ, 2, false>(f, wnew_g, zp_g, zcol, cN, cY, B->coef_p, has_pair, nz, write_f, i, W, Z, ld, S);
+      nka_pass_b_elem<NZ, 2, false>(Vec<2>::ld_plain(f, i), f, wnew_g, zp_g, zcol, cN, cY, B->coef_p, has_pair, nz, write_f, i, W, Z, ld, S);
     return;
   }
 

@@ -216,6 +216,40 @@ def test_host_pointer_path_large_pinned_matches_device_path():
     a.delete(); b.delete()
 
 
+_PAGEABLE_HOST = r"""
+import sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch
+from nka_b200 import NKA
+n, mvec = (1 << 24) + 3, 3
+g = torch.Generator(device="cuda").manual_seed(5)
+a, b = NKA(n, mvec, 0.01), NKA(n, mvec, 0.01)
+host = np.empty(n, dtype=np.float64)            # malloc'ed: what src-C/nka_example.c:139 passes
+for t in range(mvec + 4):
+    f = torch.rand(n, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    host[:] = f.cpu().numpy()
+    a.accel_update(f)
+    b.accel_update(host)
+    got = torch.from_numpy(host).cuda()
+    assert float((got - f).norm() / f.norm()) <= 1e-13, t
+    assert a.num_vec() == b.num_vec()
+a.delete(); b.delete()
+print("pageable host path ok")
+"""
+
+
+@pytest.mark.parametrize("threads", ["0", "3"])
+def test_host_pointer_path_large_pageable_matches_device_path(threads):
+    """n = 2^24 + 3 from PAGEABLE host memory in 16 chunks of 8 MiB: the host threads copy each chunk through
+    three pinned slots (nka_hostcopy.h; NKA_HOST_THREADS=0: the driver's own staging) -- same decisions and
+    results as the device-pointer path on the same inputs."""
+    env = dict(os.environ, NKA_HOST_CHUNK_BYTES=str(8 << 20), NKA_HOST_THREADS=threads)
+    r = subprocess.run([sys.executable, "-c", _PAGEABLE_HOST % {"root": ROOT}], env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "pageable host path ok" in r.stdout
+
+
 @pytest.mark.parametrize("name", ["iid_n1000_m10", "picard_n500_m5_v2", "relax_restart_n96_m4", "repeats_n128_m4"])
 def test_dot_product_hook_is_used_for_the_global_sum(name):
     """nka_init(vlen, mvec, vtol, dp) with a non-NULL dp (src-C/...c:227-231): each partial dot product
