@@ -660,16 +660,17 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
 #define NKA_HOST_MAX_CHUNKS 16
 
 // Host threads for pageable callers (nka_hostcopy.h).  NKA_HOST_THREADS: helpers besides the calling
-// thread (default: up to 7, a quarter of the cores; 0 = leave pageable memory to the driver's own staging).
+// thread (default 3: the copies are bound by host memory bandwidth, 7 / 11 / 15 helpers were no faster on the
+// 16-core bench box, gpurun_out/bench_ht*_r2z.json; 0 = leave pageable memory to the driver's own staging).
 static NkaHostCopier* host_copier()
 {
   static NkaHostCopier* c = nullptr;
   static bool decided = false;
   if (!decided) {
     decided = true;
-    int nt = (int)std::thread::hardware_concurrency() / 4;
-    if (nt > 7) nt = 7;
-    if (nt < 1) nt = 1;
+    int nt = (int)std::thread::hardware_concurrency() - 1;
+    if (nt > 3) nt = 3;
+    if (nt < 0) nt = 0;
     if (const char* e = getenv("NKA_HOST_THREADS")) nt = atoi(e);
     if (nt > 0) c = new NkaHostCopier(nt);           // lives until the process ends
   }
