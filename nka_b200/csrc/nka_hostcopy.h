@@ -42,7 +42,7 @@ class NkaHostCopier {
   {
     const size_t parts = workers_.size() + 1;
     if (parts == 1 || bytes < (size_t)(4u << 20)) { memcpy(dst, src, bytes); return; }
-    const size_t per = ((bytes / parts) + 4095) & ~(size_t)4095;
+    const size_t per = (((bytes + parts - 1) / parts) + 4095) & ~(size_t)4095;   // parts * per >= bytes
     {
       std::lock_guard<std::mutex> lk(m_);
       dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; per_ = per;
