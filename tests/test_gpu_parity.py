@@ -240,10 +240,10 @@ print("pageable host path ok")
 
 @pytest.mark.parametrize("threads", ["0", "3"])
 def test_host_pointer_path_large_pageable_matches_device_path(threads):
-    """n = 2^24 + 3 from PAGEABLE host memory in 16 chunks of 8 MiB: the host threads copy each chunk through
-    three pinned slots (nka_hostcopy.h; NKA_HOST_THREADS=0: the driver's own staging) -- same decisions and
-    results as the device-pointer path on the same inputs."""
-    env = dict(os.environ, NKA_HOST_CHUNK_BYTES=str(8 << 20), NKA_HOST_THREADS=threads)
+    """n = 2^24 + 3 from PAGEABLE host memory in 15 chunks of 9 MiB + 128 B (a size the threads' shares do not
+    divide): the host threads copy each chunk through three pinned slots (nka_hostcopy.h; NKA_HOST_THREADS=0: the
+    driver's own staging) -- same decisions and results as the device-pointer path on the same inputs."""
+    env = dict(os.environ, NKA_HOST_CHUNK_BYTES=str((9 << 20) + 128), NKA_HOST_THREADS=threads)
     r = subprocess.run([sys.executable, "-c", _PAGEABLE_HOST % {"root": ROOT}], env=env, capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
