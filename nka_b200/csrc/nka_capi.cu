@@ -724,6 +724,9 @@ extern "C" void nka_accel_update_host(NKA st, double* f)
   // Pageable caller memory: the host threads copy each chunk into / out of a pinned slot (three slots,
   // so a slot is refilled while the previous two are on the bus); page-locked memory goes straight to the DMA engines.
   NkaHostCopier* hc = host_pointer_is_pageable(f) ? host_copier() : nullptr;
+  // one process per GPU: with fewer than four cores per rank the ranks' copy threads only fight over the cores and
+  // the memory bus (8 ranks on 16 cores: 91 ms per update against 72 ms with the driver's staging, profiles/r2ab_* vs r2k_*)
+  if (hc && st->comm && (int)std::thread::hardware_concurrency() / st->comm->nranks < 4) hc = nullptr;
   constexpr int NS = 3;
   if (hc) {
     const size_t need = per * sizeof(double);
