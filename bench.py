@@ -334,6 +334,61 @@ def parity_probe(world, rank, local_rank):
     return report if rank == 0 else None
 
 
+def example_probe(world, rank, local_rank):
+    """The example's physics on the N ranks' row slabs (BASELINE.json configs[3] in miniature, 200 x 131: odd slab
+    sizes at every N) against the CPU oracle on rank 0: u <- u - z and the fused residual (halo rows from the
+    neighbouring ranks, global norm), three SSOR sweeps that cross every slab boundary strip by strip through NVLink
+    peer memory, and a second application -- all np.array_equal to the serial loops.  Returns the dict for the JSON
+    line on rank 0 (None elsewhere); ok=False fails the run."""
+    import numpy as np
+    import torch.distributed as dist
+    from nka_b200.example import System, distributed_system, FIELD_U, FIELD_R, FIELD_Z
+    nx, ny, nsweep = 200, 131, 3
+    rng = np.random.default_rng(42)
+    u = rng.uniform(0.0, 0.3, (ny, nx))
+    z = rng.uniform(-0.01, 0.01, (ny, nx))
+    sy = distributed_system(0.02, nx, ny, scaling=1, device=local_rank) if world > 1 else System(0.02, nx, ny, scaling=1, device=local_rank)
+    k0, k1 = (sy.k0, sy.k1) if world > 1 else (0, ny)
+    sy.set(FIELD_U, u[k0:k1])
+    sy.set(FIELD_Z, z[k0:k1])
+    mine = {"rows": (k0, k1), "rnorm": sy.residual(subtract_z=True), "u": sy.get(FIELD_U), "r": sy.get(FIELD_R)}
+    err = 0
+    try:
+        sy.pc_ssor(nsweep, 1.4)
+        mine["z"] = sy.get(FIELD_Z)
+        sy.pc_ssor(1, 1.4)
+        mine["z2"] = sy.get(FIELD_Z)
+        sy.residual(subtract_z=False)       # picks up the sweeps' device-side status ...
+        sy.pc_ssor(1, 1.4)                  # ... which the next call reports (include/nka_example.h)
+    except RuntimeError:
+        err = 1
+        mine.setdefault("z", np.zeros((k1 - k0, nx))); mine.setdefault("z2", np.zeros((k1 - k0, nx)))
+    mine["error"] = err
+    sy.delete()
+    if world > 1:
+        parts = [None] * world
+        dist.all_gather_object(parts, mine)
+    else:
+        parts = [mine]
+    if rank != 0:
+        return None
+    from oracle import api
+    orc = api.OracleSystem(nx, ny, 0.02, 1)
+    unew = u - z
+    pad = np.zeros((ny + 2, nx + 2)); pad[1:-1, 1:-1] = unew
+    r = orc.residual(pad).reshape(ny, nx)
+    want = {"u": unew, "r": r, "z": orc.pc_ssor(nsweep, 1.4, r.ravel().copy()).reshape(ny, nx),
+            "z2": orc.pc_ssor(1, 1.4, r.ravel().copy()).reshape(ny, nx)}
+    parts.sort(key=lambda d: d["rows"][0])
+    equal = {k: bool(np.array_equal(np.concatenate([d[k] for d in parts], axis=0), w)) for k, w in want.items()}
+    norms_same = all(d["rnorm"] == parts[0]["rnorm"] for d in parts)
+    norm_err = abs(parts[0]["rnorm"] - orc.norm2(r.ravel())) / parts[0]["rnorm"]
+    ok = all(equal.values()) and norms_same and norm_err <= 1e-13 and all(d["error"] == 0 for d in parts)
+    return {"grid": [nx, ny], "ranks": world, "slab_rows": [d["rows"][1] - d["rows"][0] for d in parts],
+            "bit_identical": equal, "norm_same_on_every_rank": norms_same, "norm_rel_err": norm_err,
+            "device_errors": [d["error"] for d in parts], "ok": bool(ok)}
+
+
 def time_updates(acc, pool, k, steps, stream, torch):
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
@@ -421,6 +476,17 @@ def run_ours(args):
         if int(flag.item()) == 0:
             if rank == 0:
                 print(json.dumps({"error": "parity probe failed", "parity_probe": probe}))
+            raise SystemExit(3)
+
+    ex_probe = None
+    if not args.no_probe:
+        ex_probe = example_probe(world, rank, local_rank)
+        flag = torch.tensor([1 if (ex_probe is None or ex_probe["ok"]) else 0], device="cuda")
+        if world > 1:
+            dist.broadcast(flag, src=0)
+        if int(flag.item()) == 0:
+            if rank == 0:
+                print(json.dumps({"error": "example probe failed", "example_probe": ex_probe}))
             raise SystemExit(3)
 
     n, m = args.n, args.mvec
@@ -618,7 +684,7 @@ def run_ours(args):
             "config": workload_config(args),
             "n_local": n_local,
             "comm_mode": comm_mode,
-            "parity_probe": probe,
+            "parity_probe": probe, "example_probe": ex_probe,
             "hbm_gbs": gbs, "roofline_frac_update": gbs / (peak * world),
             "roofline_update": {"algorithmic_bytes": algo, "formula": "(2M+4)*n*8", "achieved_gbs": gbs,
                                 "peak_gbs": peak * world, "frac": gbs / (peak * world),
