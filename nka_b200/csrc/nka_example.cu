@@ -213,6 +213,8 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
 #define EX_RS_MINB 4             // CTAs per SM the register budget is held to (64 registers, 32 B of spills)
 #endif
 
+template <bool V> struct ExTag { static constexpr bool value = V; };
+
 struct ResStripParams {
   ResParams p;
   int nstrips, nbands, band;     // strips of 30 columns; bands of `band` diagonals per strip
@@ -271,8 +273,20 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
       continue;
     }
 
+    // The walk, compiled twice.  IN = every cell the 32 lanes touch in this item (halo lanes and the two prologue /
+    // one epilogue diagonals included) lies inside the grid with all four neighbours present -- no boundary row or
+    // column, no neighbouring slab's edge row: all the predicates below are then true and drop out (the bulk of a
+    // large grid's items; ~100 of the general walk's ~280 instructions per step are this bookkeeping).
+    auto walk = [&](auto interior) -> double {
+    constexpr bool IN = decltype(interior)::value;
     // what a lane sees at (j, k): in-grid value, a neighbouring slab's edge row, or nothing (zeros)
     auto fetch = [&](int tau, long long base, double& ur, double& zr) {
+      if (IN) {                                                       // every lane's cell is inside the grid
+        const bool live = tau <= t1;
+        ur = live ? __ldg(U + (base + j)) : 0.0;
+        zr = (live && Zc) ? __ldg(Zc + (base + j)) : 0.0;
+        return;
+      }
       const int k = tau - j;
       const bool live = cin && tau <= t1;                             // nothing beyond the band's last step
       const bool ing = live && (unsigned)k < (unsigned)ny;
@@ -284,7 +298,7 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
       zr = (ing && Zc) ? __ldg(Zc + (base + j)) : 0.0;
     };
     auto next_base = [&](int tau, long long base) -> long long {      // wf_base(tau + 1) from wf_base(tau)
-      return (tau >= 0 && tau <= tmax - 1) ? base + wf_step(tau, nx, ny) : 0;
+      return (IN || (tau >= 0 && tau <= tmax - 1)) ? base + wf_step(tau, nx, ny) : 0;
     };
 
     // Operands are loaded a BATCH of EX_RS_PF diagonals at a time, one batch ahead of use, and handed
@@ -319,8 +333,8 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
         const int tau = tau0 + i;
         if (tau <= t1) {                                               // warp-uniform
           const int k = tau - j;
-          const bool krange = k >= kmin && k <= kmax;
-          const bool pc = cin && krange, pl = cinl && krange, pd = pc_p;
+          const bool krange = IN || (k >= kmin && k <= kmax);
+          const bool pc = IN || (cin && krange), pl = IN || (cinl && krange), pd = IN || pc_p;
           const double u_n = Zc ? __dsub_rn(cu[i], cz[i]) : cu[i];    // u = u - r : F08 :248 (z = 0 outside the grid)
           // update_system (:122-145)
           const double tc = __ddiv_rn(1.0, __dadd_rn(P.a, u_n));
@@ -335,7 +349,7 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
           const double u_r = __shfl_down_sync(0xffffffffu, u_n, 1);    // (j+1, k-1): diagonal tau
           const double axr = __shfl_down_sync(0xffffffffu, fx_n, 1);   // left face of (j+1, k-1)
           const int kc = k - 1;
-          if (mine && tau - 1 >= t0 && (unsigned)kc < (unsigned)ny) {
+          if (mine && tau - 1 >= t0 && (IN || (unsigned)kc < (unsigned)ny)) {
             const double axl = fx_p, ayd = fy_p, ayu = fy_n;
             const double ac = __dadd_rn(__dadd_rn(__dadd_rn(axl, axr), ayd), ayu);        // :142
             double r = __dmul_rn(ac, u_p);                                                  // :115-117, left to right
@@ -347,8 +361,8 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
             const long long c = base_p + j;
             P.R[c] = r; P.AXL[c] = axl; P.AYD[c] = ayd; P.AC[c] = ac;
             if (Zc) P.Unew[c] = u_p;
-            if (j == nx - 1) P.AXR[kc] = axr;
-            if (kc == ny - 1) P.AYT[j] = ayu;
+            if (!IN && j == nx - 1) P.AXR[kc] = axr;
+            if (!IN && kc == ny - 1) P.AYT[j] = ayu;
             rr = __dadd_rn(rr, __dmul_rn(r, r));
           }
           u_pp = u_p; u_p = u_n;
@@ -360,6 +374,11 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
 #pragma unroll
       for (int i = 0; i < EX_RS_PF; ++i) { cu[i] = nu[i]; cz[i] = nz[i]; }
     }
+    return rr;
+    };
+    const int js = s * EX_RS_COLS;
+    const bool interior_item = s >= 1 && js + EX_RS_COLS <= nx - 1 && (t0 - 1) - (js + EX_RS_COLS) >= 1 && t1 - (js - 1) <= ny - 1;
+    double rr = interior_item ? walk(ExTag<true>()) : walk(ExTag<false>());
     rr = ex_warp_sum(rr);
     if (lane == 0) P.partials[item] = rr;
   }
