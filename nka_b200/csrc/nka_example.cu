@@ -209,6 +209,10 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
 #ifndef EX_RS_PF
 #define EX_RS_PF 2               // diagonals per load batch
 #endif
+#ifndef EX_RS_L2D
+#define EX_RS_L2D 0              // diagonals by which prefetch.global.L2 runs ahead of the register loads; 0 = off: tried
+                                 // with 4 / 8 / 16 and 3-6 % SLOWER (profiles/r2af_residual_l2_prefetch_ab.jsonl)
+#endif
 #ifndef EX_RS_MINB
 #define EX_RS_MINB 4             // CTAs per SM the register budget is held to (64 registers, 32 B of spills)
 #endif
@@ -316,6 +320,24 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
       basef = next_base(tf, basef);
       ++tf;
     }
+    // Experiment (EX_RS_L2D > 0, off in the product build): the register loads run one batch ahead, which is less
+    // than the DRAM latency under load (ncu: 67 % of the stall samples on the load scoreboard); an L2 prefetch
+    // EX_RS_L2D diagonals further ahead was meant to turn the DRAM round trip into an L2 hit without holding
+    // registers.  Measured 3-6 % slower at every distance: the ~14 extra instructions per step cost more than the
+    // shorter wait gives back.
+    int tl2 = tf + EX_RS_L2D;
+    long long basel2 = (EX_RS_L2D > 0 && tl2 >= 0 && tl2 <= tmax) ? wf_base(tl2, nx, ny) : 0;
+    auto l2_ahead = [&]() {
+      if (EX_RS_L2D > 0) {
+        const int k = tl2 - j;
+        if (tl2 <= t1 && cin && (unsigned)k < (unsigned)ny) {
+          asm volatile("prefetch.global.L2 [%0];" :: "l"(U + (basel2 + j)));
+          if (Zc) asm volatile("prefetch.global.L2 [%0];" :: "l"(Zc + (basel2 + j)));
+        }
+        basel2 = next_base(tl2, basel2);
+        ++tl2;
+      }
+    };
 
     double u_pp = 0.0, u_p = 0.0, tx_p = 0.0, ty_p = 0.0, fx_p = 1.0, fy_p = 1.0;
     bool pc_p = false;                                                 // was (j, k-1) there: the previous step's own cell
@@ -328,6 +350,8 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
         basef = next_base(tf, basef);
         ++tf;
       }
+#pragma unroll
+      for (int i = 0; i < EX_RS_PF; ++i) l2_ahead();
 #pragma unroll
       for (int i = 0; i < EX_RS_PF; ++i) {
         const int tau = tau0 + i;
