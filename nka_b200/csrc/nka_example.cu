@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
 // Work items = (band, strip), handed out in order through an atomic counter; each item leaves its
 // own partial sum of r^2, folded in item order by the last CTA: run-to-run bit-stable.
 #define EX_RS_COLS 30
+#ifndef EX_RS_THREADS
 #define EX_RS_THREADS 256
+#endif
 #ifndef EX_RS_PF
 #define EX_RS_PF 2               // diagonals per load batch
 #endif
@@ -214,7 +216,9 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
                                  // with 4 / 8 / 16 and 3-6 % SLOWER (profiles/r2af_residual_l2_prefetch_ab.jsonl)
 #endif
 #ifndef EX_RS_MINB
-#define EX_RS_MINB 4             // CTAs per SM the register budget is held to (64 registers, 32 B of spills)
+#define EX_RS_MINB 3             // CTAs per SM the register budget is held to: 78 registers, NO spills.  With 4 (64 registers)
+                                 // the spilled prefetch values made the warp wait for its loads at once: 57 % of all stall
+                                 // samples sat on two spill instructions (profiles/r2ae_*); 3 is 6-8 % faster (r2ag)
 #endif
 
 template <bool V> struct ExTag { static constexpr bool value = V; };

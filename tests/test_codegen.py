@@ -79,3 +79,15 @@ def test_ssor_sweep_hot_loops(objdir):
         assert "MEMBAR" not in sass                           # barriers order the hand-over; a fence stalls on the cp.asyncs in flight
         assert "LDGSTS" in sass and "BAR.ARV" in sass and "SHFL" in sass
         assert "MUFU.RCP64H" in sass                          # the reciprocal half of the split division (copier warp)
+
+
+def test_residual_strip_kernel_does_not_spill(objdir):
+    """The residual walk keeps its prefetched operands in registers: a spilled prefetch value makes the warp wait
+    for its loads at once (57 % of all stall samples in the 64-register build, profiles/r2ae_residual_strip_8192_ncu.txt)."""
+    obj = os.path.join(objdir, "nka_example.o")
+    res = _res_usage(obj)
+    name = _find(res, "_Z24ex_residual_strip_kernel")[0]
+    assert res[name]["stack"] == 0 and res[name]["local"] == 0, res[name]
+    assert res[name]["reg"] <= 85, res[name]                  # three CTAs of 256 threads per SM
+    sass = _sass(obj, name)
+    assert "STL" not in sass and "LDL" not in sass
