@@ -211,6 +211,9 @@ __global__ void __launch_bounds__(EX_RES_THREADS) ex_residual_kernel(ResParams P
 #ifndef EX_RS_PF
 #define EX_RS_PF 2               // diagonals per load batch
 #endif
+#ifndef EX_RS_DEPTH
+#define EX_RS_DEPTH 2            // load batches in flight ahead of the one being used (1: only the next batch)
+#endif
 #ifndef EX_RS_L2D
 #define EX_RS_L2D 0              // diagonals by which prefetch.global.L2 runs ahead of the register loads; 0 = off: tried
                                  // with 4 / 8 / 16 and 3-6 % SLOWER (profiles/r2af_residual_l2_prefetch_ab.jsonl)
@@ -316,6 +319,7 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
     // that version, profiles/r2e_residual_strip_ncu.txt.  A cp.async ring instead moved the stalls
     // to the memory-instruction queue, next to the step's eight shuffles: profiles/r2h_*.)
     double cu[EX_RS_PF], cz[EX_RS_PF], nu[EX_RS_PF], nz[EX_RS_PF];
+    double mu[EX_RS_DEPTH > 1 ? EX_RS_PF : 1], mz[EX_RS_DEPTH > 1 ? EX_RS_PF : 1];   // the batch after next (EX_RS_DEPTH = 2)
     int tf = t0 - 1;
     long long basef = (tf >= 0 && tf <= tmax) ? wf_base(tf, nx, ny) : 0;
 #pragma unroll
@@ -323,6 +327,14 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
       fetch(tf, basef, cu[i], cz[i]);
       basef = next_base(tf, basef);
       ++tf;
+    }
+    if (EX_RS_DEPTH > 1) {
+#pragma unroll
+      for (int i = 0; i < EX_RS_PF; ++i) {
+        fetch(tf, basef, nu[i], nz[i]);
+        basef = next_base(tf, basef);
+        ++tf;
+      }
     }
     // Experiment (EX_RS_L2D > 0, off in the product build): the register loads run one batch ahead, which is less
     // than the DRAM latency under load (ncu: 67 % of the stall samples on the load scoreboard); an L2 prefetch
@@ -349,8 +361,9 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
     double rr = 0.0;
     for (int tau0 = t0 - 1; tau0 <= t1; tau0 += EX_RS_PF) {
 #pragma unroll
-      for (int i = 0; i < EX_RS_PF; ++i) {                             // the next batch, all loads back to back
-        fetch(tf, basef, nu[i], nz[i]);
+      for (int i = 0; i < EX_RS_PF; ++i) {                             // a batch ahead, all loads back to back
+        if (EX_RS_DEPTH > 1) fetch(tf, basef, mu[i], mz[i]);
+        else fetch(tf, basef, nu[i], nz[i]);
         basef = next_base(tf, basef);
         ++tf;
       }
@@ -400,7 +413,10 @@ __global__ void __launch_bounds__(EX_RS_THREADS, EX_RS_MINB) ex_residual_strip_k
         }
       }
 #pragma unroll
-      for (int i = 0; i < EX_RS_PF; ++i) { cu[i] = nu[i]; cz[i] = nz[i]; }
+      for (int i = 0; i < EX_RS_PF; ++i) {
+        cu[i] = nu[i]; cz[i] = nz[i];
+        if (EX_RS_DEPTH > 1) { nu[i] = mu[i]; nz[i] = mz[i]; }
+      }
     }
     return rr;
     };
