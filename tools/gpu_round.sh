@@ -15,9 +15,9 @@ bench)
   cut -c1-400 gpurun_out/bench_$tag.json; tail -3 gpurun_out/bench_$tag.err ;;
 ncu)
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$tag.csv \
-     python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_list_$tag.log 2>&1
+     python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-probe --no-sweep > gpurun_out/ncu_list_$tag.log 2>&1
   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:nka_pass -s 30 -c 4 -f -o gpurun_out/prof_$tag \
-     python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline > gpurun_out/ncu_full_$tag.log 2>&1
+     python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu-baseline --no-probe --no-sweep > gpurun_out/ncu_full_$tag.log 2>&1
   ls -la gpurun_out/prof_$tag.ncu-rep ;;
 multi)
   ng=${NGPUS:-2}
