@@ -664,16 +664,14 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
 // 16-core bench box, gpurun_out/bench_ht*_r2z.json; 0 = leave pageable memory to the driver's own staging).
 static NkaHostCopier* host_copier()
 {
-  static NkaHostCopier* c = nullptr;
-  static bool decided = false;
-  if (!decided) {
-    decided = true;
+  // (function-local static: initialised once, thread-safe)
+  static NkaHostCopier* const c = [] () -> NkaHostCopier* {
     int nt = (int)std::thread::hardware_concurrency() - 1;
     if (nt > 3) nt = 3;
     if (nt < 0) nt = 0;
     if (const char* e = getenv("NKA_HOST_THREADS")) nt = atoi(e);
-    if (nt > 0) c = new NkaHostCopier(nt);           // lives until the process ends
-  }
+    return nt > 0 ? new NkaHostCopier(nt) : nullptr;     // lives until the process ends
+  }();
   return c;
 }
 
