@@ -722,9 +722,10 @@ extern "C" void nka_accel_update_host(NKA st, double* f)
   // Pageable caller memory: the host threads copy each chunk into / out of a pinned slot (three slots,
   // so a slot is refilled while the previous two are on the bus); page-locked memory goes straight to the DMA engines.
   NkaHostCopier* hc = host_pointer_is_pageable(f) ? host_copier() : nullptr;
-  // one process per GPU: with fewer than four cores per rank the ranks' copy threads only fight over the cores and
-  // the memory bus (8 ranks on 16 cores: 91 ms per update against 72 ms with the driver's staging, profiles/r2ab_* vs r2k_*)
-  if (hc && st->comm && (int)std::thread::hardware_concurrency() / st->comm->nranks < 4) hc = nullptr;
+  // one process per GPU on a shared box: the ranks' copy threads compete for the same cores and the same host
+  // memory bus and lose against the driver's own staging (8 ranks: 91 ms per update against 72 ms on 16- and
+  // 32-core boxes, profiles/r2ab_*, r2am vs r2k_*): the host threads are for the single-process caller
+  if (hc && st->comm && st->comm->nranks > 1) hc = nullptr;
   constexpr int NS = 3;
   if (hc) {
     const size_t need = per * sizeof(double);
