@@ -277,3 +277,37 @@ def test_shim_check_really_rejects_a_width_mismatch(tmp_path):
                         "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "bad.o")],
                        capture_output=True, text=True)
     assert r.returncode != 0
+
+
+def test_fortran_sources_parse_with_f2py_crackfortran():
+    """No Fortran compiler in the image; numpy's f2py carries a Fortran 90 parser (crackfortran).  It is not a
+    compiler -- it does not check types or generic resolution -- but it does find unbalanced blocks, broken
+    continuation lines and malformed declarations: every module must parse, and in the two interface modules it
+    must see exactly the bind(C) procedures the ABI checks above work from."""
+    import contextlib
+    import glob
+    import io
+    from numpy.f2py import crackfortran
+    fdir = os.path.join(ROOT, "nka_b200", "fortran")
+    files = sorted(glob.glob(os.path.join(fdir, "*.F90")) + glob.glob(os.path.join(fdir, "*", "*.F90")))
+    assert len(files) == 6
+    want_modules = {"nka_b200_c.F90": "nka_b200_c", "nka_example_c.F90": "nka_example_c", "gpu_vector_type.F90": "gpu_vector_type"}
+    for f in files:
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf), contextlib.redirect_stderr(buf):
+            blocks = crackfortran.crackfortran([f])
+        mods = [b for b in blocks if b.get("block") == "module"]
+        assert len(mods) == 1, (f, [b.get("block") for b in blocks])
+        assert mods[0]["name"] == want_modules.get(os.path.basename(f), "nka_type"), f
+        if os.path.basename(f) in ("nka_b200_c.F90", "nka_example_c.F90"):
+            procs = []
+
+            def walk(body):
+                for b in body:
+                    if b.get("block") in ("function", "subroutine"):
+                        procs.append(b["name"])
+                    walk(b.get("body", []))
+            walk(mods[0]["body"])
+            text = re.sub(r"&\s*\n\s*", " ", open(f).read())
+            declared = re.findall(r"(?:function|subroutine)\s+(\w+)\s*\([^)]*\)\s*bind\(C", text, re.I)
+            assert sorted(p.lower() for p in procs) == sorted(d.lower() for d in declared), f
