@@ -30,6 +30,7 @@
 #include "../../include/nka_example.h"
 #include "nka_internal.h"
 #include "nka_state.h"      // NKA_MAX_RANKS
+#include "nka_res_items.h"
 
 #if defined(__CUDACC__)
 #define EX_HD __host__ __device__ __forceinline__
@@ -1058,23 +1059,13 @@ extern "C" NKASYS nka_system_init_slab(int nx, int ny_global, int k0, int k1, do
     sy->rs_bands = ((sy->rs_absolute ? nx + ny - 1 : ndiag) + band - 1) / band;
     size_t items = (size_t)sy->rs_strips * sy->rs_bands;
     if (sy->rs_absolute) {
-      // (band, strip) pairs that hold cells: strip s has cells on diagonals [30 s, 30 s + 29 + ny), band b is [b B, (b+1) B)
-      std::vector<unsigned> first(sy->rs_bands + 1);
-      std::vector<int> s_lo(sy->rs_bands);
-      size_t count = 0;
-      for (int b = 0; b < sy->rs_bands; ++b) {
-        const long long lo_t = (long long)b * band, hi_t = lo_t + band;           // [lo_t, hi_t)
-        long long s0 = lo_t - (EX_RS_COLS - 1) - ny;                                // 30 s > s0  <=>  the strip has not ended before the band
-        s0 = s0 < 0 ? 0 : s0 / EX_RS_COLS + 1;
-        long long s1 = (hi_t - 1) / EX_RS_COLS;                                     // 30 s <= hi_t - 1  <=>  the strip has started by the band's end
-        if (s1 > sy->rs_strips - 1) s1 = sy->rs_strips - 1;
-        first[b] = (unsigned)count;
-        s_lo[b] = (int)s0;
-        if (s1 >= s0) count += (size_t)(s1 - s0 + 1);
-      }
-      first[sy->rs_bands] = (unsigned)count;
-      items = count;
-      sy->rs_items = (unsigned)count;
+      // (band, strip) pairs that hold cells, numbered band by band: nka_res_items.h
+      const NkaResItems ri = nka_res_items(nx, ny, EX_RS_COLS, band);
+      NKA_REQUIRE(ri.nbands == sy->rs_bands, "nka_system_init: residual item geometry");
+      const std::vector<unsigned>& first = ri.first;
+      const std::vector<int>& s_lo = ri.s_lo;
+      items = ri.count;
+      sy->rs_items = (unsigned)ri.count;
       CUDA_CHECK(cudaMalloc(&sy->rs_first_item, first.size() * sizeof(unsigned)));
       CUDA_CHECK(cudaMalloc(&sy->rs_first_strip, s_lo.size() * sizeof(int)));
       CUDA_CHECK(cudaMemcpy(sy->rs_first_item, first.data(), first.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
