@@ -42,6 +42,7 @@ class NkaHostCopier {
   {
     const size_t parts = workers_.size() + 1;
     if (parts == 1 || bytes < (size_t)(4u << 20)) { memcpy(dst, src, bytes); return; }
+    std::lock_guard<std::mutex> one_job(job_);          // the pool holds one job: callers on different threads take turns
     const size_t per = (((bytes + parts - 1) / parts) + 4095) & ~(size_t)4095;   // parts * per >= bytes
     {
       std::lock_guard<std::mutex> lk(m_);
@@ -82,7 +83,7 @@ class NkaHostCopier {
   }
 
   std::vector<std::thread> workers_;
-  std::mutex m_;
+  std::mutex m_, job_;
   std::condition_variable cv_, done_;
   unsigned long long generation_ = 0;
   bool stop_ = false;

@@ -4,6 +4,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <functional>
+#include <thread>
 #include <vector>
 
 #include "../../nka_b200/csrc/nka_hostcopy.h"
@@ -44,6 +46,23 @@ int main(int argc, char** argv)
           if (dst[i] != 0xEE) { printf("FAIL underrun bytes=%zu\n", bytes); return 1; }
         ++rounds;
       }
+  // two application threads sharing the pool (two handles updated from two host threads): copies take turns
+  {
+    const size_t bytes = (24u << 20) + 8;
+    std::vector<unsigned char> s2(bytes), d2(bytes), s3(bytes), d3(bytes);
+    for (size_t i = 0; i < bytes; ++i) { s2[i] = (unsigned char)mix(i); s3[i] = (unsigned char)mix(i + 77); }
+    int bad = 0;
+    auto job = [&](const std::vector<unsigned char>& s, std::vector<unsigned char>& d) {
+      for (int r = 0; r < 6; ++r) {
+        memset(d.data(), 0, bytes);
+        hc.copy(d.data(), s.data(), bytes);
+        if (memcmp(d.data(), s.data(), bytes) != 0) ++bad;
+      }
+    };
+    std::thread a(job, std::cref(s2), std::ref(d2)), b(job, std::cref(s3), std::ref(d3));
+    a.join(); b.join();
+    if (bad) { printf("FAIL concurrent callers: %d bad copies\n", bad); return 1; }
+  }
   printf("hostcopy ok: %d copies with %d threads\n", rounds, hc.threads());
   return 0;
 }
