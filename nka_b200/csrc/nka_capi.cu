@@ -661,7 +661,7 @@ extern "C" void nka_accel_update_dev(NKA st, double* f)
 
 // Host threads for pageable callers (nka_hostcopy.h).  NKA_HOST_THREADS: helpers besides the calling
 // thread (default 3: the copies are bound by host memory bandwidth, 7 / 11 / 15 helpers were no faster on the
-// 16-core bench box, gpurun_out/bench_ht*_r2z.json; 0 = leave pageable memory to the driver's own staging).
+// 16-core bench box, profiles/r2z_host_threads_sweep.txt; 0 = leave pageable memory to the driver's own staging).
 static NkaHostCopier* host_copier()
 {
   // (function-local static: initialised once, thread-safe)
